@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — voxel-updates/s of the fs3d step on N B200s, as one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size S] [--impl ours|reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL halo exchange)
+
+Workload (BASELINE.json configs[3], the one the 60 %-of-roofline target is quoted on): a 2048³
+MIXED_NOISE scene (stone floor + obstacles + sand box + water box + sand/water noise in the upper
+half), generated on device, strong-scaled as z-slabs over the ranks.  One step = one full
+SCHEDULE.md step of every voxel.  The grid (8 GiB per buffer) is far larger than the 126 MB L2, so
+no L2 flush is needed between timed steps.
+
+  value      device-resident throughput: nx·ny·nz·K / (max over ranks of the CUDA-event time of K steps)
+  e2e        same metric through the C ABI with HOST buffers: every step uploads the grid from pinned
+             host memory, steps, and downloads the result (PCIe inside the timed region)
+  roofline   2 B per voxel-update (1 B read + 1 B written) over the measured HBM copy peak
+  cpu_baseline  the CPU oracle (a builder-written port: the reference has NO implementation of this
+             path) timed on this box's host cores on a bounded sample
+
+--impl reference times that same CPU oracle on all host threads (rank 0 only) on a bounded sample
+of the same workload: it is the only "reference CPU implementation" that can exist.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxel-updates/s"
+SCENE_MIXED_NOISE = 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(nx, ny, nz_sample, steps, seed=1):
+    """voxel-updates/s of the CPU oracle on a bounded slab sample of the workload."""
+    from oracle import oracle
+    import numpy as np
+    full_nz = nx  # cubic workload
+    zlo = full_nz // 2 - nz_sample // 2      # straddles the noisy upper half and the obstacles
+    g = oracle.generate(nx, ny, full_nz, SCENE_MIXED_NOISE, 1, zlo, zlo + nz_sample)
+    oracle.step(g, seed, 0)                   # warm-up (page faults, OpenMP pool)
+    t0 = time.perf_counter()
+    for t in range(1, 1 + steps):
+        oracle.step(g, seed, t)
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    omp = os.environ.get("OMP_NUM_THREADS")
+    if omp:
+        cores = min(cores, int(omp))
+    return nx * ny * nz_sample * steps / dt, cores, dt, f"{nx}x{ny}x{nz_sample} slab of the {nx}^3 MIXED_NOISE scene, {steps} steps"
+
+
+def reference_arm(args):
+    """--impl reference: the CPU oracle (kind "port") on all host threads, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.size
+    nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))        # ~64 Mi voxels per step
+    rates = []
+    for _ in range(args.warmup):
+        cpu_oracle_rate(n, n, nz_sample, 1)
+    t0 = time.perf_counter()
+    total_ms = 0.0
+    cores = 1
+    sample = ""
+    for _ in range(args.steps):
+        r, cores, dt, sample = cpu_oracle_rate(n, n, nz_sample, 1)
+        rates.append(r)
+        total_ms += dt * 1e3
+    value = sum(rates) / len(rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{n}^3 MIXED_NOISE scene (BASELINE configs[3]); CPU oracle on a bounded sample",
+                   "grid": [n, n, n], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "voxel-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "the reference has no CPU update to time (SURVEY.md §0); this is the builder-written "
+                                 "CPU oracle of the same schedule, OpenMP over z"},
+        "e2e": {"value": value, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fallingsand3d_b200 as fs3d
+    from fallingsand3d_b200 import build as fsbuild, _lib
+    from fallingsand3d_b200.slab import SlabWorld
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libfs3d has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if rank == 0:
+        fsbuild.build()
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    _lib.load()
+
+    n = args.size
+    K, Wm = args.steps, max(args.warmup, 3)
+    hbm_peak, peak_src = peaks()
+    voxels = n * n * n
+
+    if world_size == 1:
+        w = fs3d.VoxelWorld(n, n, n, seed=1)
+        w.generate(SCENE_MIXED_NOISE, 1)
+        h0 = w.histogram()
+        w.step(Wm)
+        w.sync()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ms, launches = w.step_timed(K)
+        clocks = sampler.stop()
+        assert np.array_equal(w.histogram(), h0), "material counts changed: invalid run"
+        digest = w.digest()
+    else:
+        sw = SlabWorld(n, n, n, seed=1)
+        sw.generate(SCENE_MIXED_NOISE, 1)
+        h0 = sw.histogram()
+        sw.step(Wm)
+        sw.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st = sw.engine.stream
+        ev0.record(st)
+        sw.step(K)
+        ev1.record(st)
+        sw.sync()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        clocks = sampler.stop() if rank == 0 else None
+        assert np.array_equal(sw.histogram(), h0), "material counts changed: invalid run"
+        digest = sw.digest()
+        # kernels per step per rank: 2 edge launches + 1 interior (NCCL's own kernels not counted)
+        launches = 3 * K
+
+    value = voxels * K / (ms * 1e-3)
+    achieved = 2.0 * voxels * K / (ms * 1e-3) / 1e9 / world_size     # per-GPU algorithmic GB/s
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region (N = 1 path) ----
+    e2e = None
+    if world_size == 1:
+        host = torch.empty((n, n, n), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        w.download(hv)
+        ke = max(1, min(args.e2e_steps, K))
+        w.upload(hv); w.step(1); w.download(hv)          # warm-up of the copy path
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            w.upload(hv)
+            w.step(1)
+            w.download(hv)                                # synchronous: returns when the result is on the host
+        dt = time.perf_counter() - t0
+        e2e = {"value": voxels * ke / dt, "unit": "voxel-updates/s", "h2d_bytes_per_step": voxels,
+               "d2h_bytes_per_step": voxels, "steps": ke, "ms_per_step": dt * 1e3 / ke,
+               "note": "fs3d_upload(pinned host grid) + fs3d_step(1) + fs3d_download per step, wall clock"}
+        del host
+        w.close()
+    else:
+        # per rank: upload its slab, step with halo exchange, download its slab
+        zb, ze = sw.z_begin, sw.z_end
+        host = torch.empty((ze - zb, n, n), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        hv[...] = sw.download()
+        ke = max(1, min(args.e2e_steps, K))
+        sw.upload(hv); sw.step(1); hv[...] = sw.download()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            sw.upload(hv)
+            sw.step(1)
+            sw.engine.world.download(hv)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": voxels * ke / dt, "unit": "voxel-updates/s", "h2d_bytes_per_step": voxels,
+               "d2h_bytes_per_step": voxels, "steps": ke, "ms_per_step": dt * 1e3 / ke,
+               "note": "per rank: fs3d_upload(pinned slab) + slab step with NCCL halo exchange + fs3d_download"}
+        sw.close()
+
+    if rank != 0:
+        if world_size > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
+    cpu = None
+    if world_size == 1 and not args.no_cpu:
+        nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))
+        rate, cores, dt, sample = cpu_oracle_rate(n, n, nz_sample, args.cpu_steps)
+        cpu = {"value": rate, "unit": "voxel-updates/s", "cores": cores, "kind": "port", "sample": sample,
+               "seconds": dt, "note": "builder-written CPU oracle of the same schedule (the reference has no CPU "
+                                      "update, SURVEY.md §0), OpenMP over z"}
+
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(str(n))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"{n}^3 MIXED_NOISE scene (BASELINE configs[3]: 2048^3 mixed sand/water/stone), "
+                               f"generated on device, skipping off",
+                   "grid": [n, n, n], "parallelism": f"z-slabs x{world_size}" if world_size > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (grid %.1f GiB per buffer vs 126 MB L2); no flush" % (voxels / 2**30),
+                   "digest": hex(digest)},
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_voxel_update": 2, "kernel": "fs3d::step_kernel"},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+"""Builds libfs3d.so (hand-written sm_100a CUDA + C ABI) in-tree with nvcc.
+
+No reference counterpart: the reference's only build is its Vulkan/SDL CMake
+(/root/reference/CMakeLists.txt:4-46), which has no CUDA target.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libfs3d.so")
+SOURCES = [os.path.join(CSRC, "fs3d.cu")]
+HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "aux_kernels.cuh", "step_kernel.cuh", "raymarch.cuh")] + [
+    os.path.join(HERE, "..", "include", "fs3d.h")
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-Xptxas", "-v",
+    "--fmad=false",  # raymarch parity: no silent FMA contraction anywhere in this TU (integer kernels unaffected)
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libfs3d.so")
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

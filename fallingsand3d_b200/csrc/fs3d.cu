@@ -1,0 +1,780 @@
+// fs3d.cu — libfs3d: world/slab management and the C ABI declared in include/fs3d.h.
+//
+// The reference has no voxel world; this library is what its frame loop
+// (/root/reference/src/engine/engine.cpp:59-70) would call once per frame, and what its material
+// binding builder (/root/reference/src/engine/rendering/materials.cpp:388-418) would be handed a
+// volume by.  No CPU fallback exists anywhere in this file: without a CUDA device every
+// computing entry point fails with FS3D_ERR_CUDA.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "aux_kernels.cuh"
+#include "step_kernel.cuh"
+#include "raymarch.cuh"
+
+namespace fs3d {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+constexpr int STEP_THREADS = 128;
+
+struct Slab {
+    int device = 0;
+    uint32_t z0 = 0, nzl = 0;         // global planes [z0, z0 + nzl)
+    uint8_t *buf[2] = {nullptr, nullptr};   // (nzl + 2) planes each; plane 0 / nzl+1 are ghosts
+    size_t bytes = 0;
+    cudaStream_t s_main = nullptr, s_comm = nullptr;
+    cudaEvent_t ev_edges = nullptr, ev_done = nullptr, ev_halo_lo = nullptr, ev_halo_hi = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    unsigned long long *d_scratch = nullptr;   // 256 + 1 u64 + 1 u32 flag
+    uint8_t *d_img = nullptr; size_t img_bytes = 0;
+    float *d_palette = nullptr;
+    int num_sms = 0;
+    int blocks_per_sm[3][2][2] = {};   // [Jidx][OX][TODD]
+    // settled-tile skipping
+    uint8_t *d_skip = nullptr;
+    uint32_t *d_last_active = nullptr;
+    unsigned long long *d_tiles_run = nullptr;
+    uint32_t nztiles = 0, nytiles = 0;
+};
+
+}  // namespace fs3d
+
+struct fs3d_world {
+    fs3d_desc desc{};
+    std::vector<fs3d::Slab> slabs;
+    std::vector<int32_t> devices;
+    int cur = 0;                 // index of the front buffer
+    uint64_t step = 0;
+    bool external = false;       // created by fs3d_create_slab: caller exchanges halos
+    bool halo_pending = false;   // in-process: ghost planes of `cur` are being filled on s_comm
+    uint64_t launches = 0;       // kernels launched since creation
+    int jidx = 0;                // 0: J=1, 1: J=2, 2: J=4
+    uint32_t lpr = 32, groups = 1;
+    bool palette_dirty = true;
+    float palette[256 * 4];
+    int edges_phase = 0;         // external stepping protocol state
+};
+
+namespace fs3d {
+
+// ---- kernel dispatch ----------------------------------------------------------------------------
+typedef void (*StepFn)(const StepParams);
+static StepFn step_fn(int jidx, int ox, int todd) {
+    static StepFn tab[3][2][2] = {
+        {{step_kernel<1, 0, 0, STEP_THREADS>, step_kernel<1, 0, 1, STEP_THREADS>},
+         {step_kernel<1, 1, 0, STEP_THREADS>, step_kernel<1, 1, 1, STEP_THREADS>}},
+        {{step_kernel<2, 0, 0, STEP_THREADS>, step_kernel<2, 0, 1, STEP_THREADS>},
+         {step_kernel<2, 1, 0, STEP_THREADS>, step_kernel<2, 1, 1, STEP_THREADS>}},
+        {{step_kernel<4, 0, 0, STEP_THREADS>, step_kernel<4, 0, 1, STEP_THREADS>},
+         {step_kernel<4, 1, 0, STEP_THREADS>, step_kernel<4, 1, 1, STEP_THREADS>}},
+    };
+    return tab[jidx][ox][todd];
+}
+
+static size_t plane_bytes(const fs3d_world *w) { return (size_t)w->desc.nx * w->desc.ny; }
+static uint8_t *owned_ptr(const fs3d_world *w, const Slab &s, int b) { return s.buf[b] + plane_bytes(w); }
+
+static int check_dims(const fs3d_desc *d) {
+    if (!d) return fail(FS3D_ERR_INVALID_ARG, "desc is NULL");
+    if (d->nx == 0 || d->ny == 0 || d->nz == 0) return fail(FS3D_ERR_BAD_DIMS, "grid dimensions must be non-zero");
+    if (d->nx % 32 != 0) return fail(FS3D_ERR_BAD_DIMS, "nx must be a multiple of 32");
+    if (d->nx > 4096) return fail(FS3D_ERR_BAD_DIMS, "nx must be <= 4096");
+    return FS3D_OK;
+}
+
+static int init_slab(fs3d_world *w, Slab &s) {
+    FS3D_CUDA(cudaSetDevice(s.device));
+    const size_t pb = plane_bytes(w);
+    s.bytes = pb * ((size_t)s.nzl + 2);
+    for (int b = 0; b < 2; ++b) FS3D_CUDA(cudaMalloc(&s.buf[b], s.bytes));
+    FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_main, cudaStreamNonBlocking));
+    FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
+    cudaEvent_t *evs[] = {&s.ev_edges, &s.ev_done, &s.ev_halo_lo, &s.ev_halo_hi};
+    for (auto e : evs) FS3D_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    FS3D_CUDA(cudaEventCreate(&s.ev_t0));
+    FS3D_CUDA(cudaEventCreate(&s.ev_t1));
+    FS3D_CUDA(cudaMalloc(&s.d_scratch, 260 * sizeof(unsigned long long)));
+    FS3D_CUDA(cudaMalloc(&s.d_palette, 256 * 4 * sizeof(float)));
+    FS3D_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, s.device));
+    for (int ox = 0; ox < 2; ++ox)
+        for (int td = 0; td < 2; ++td) {
+            int nb = 0;
+            FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td), STEP_THREADS, 0));
+            s.blocks_per_sm[w->jidx][ox][td] = std::max(nb, 1);
+        }
+    // both buffers start as EMPTY with STONE ghost planes (closed box / not-yet-exchanged halo)
+    for (int b = 0; b < 2; ++b) {
+        FS3D_CUDA(cudaMemsetAsync(s.buf[b], 0, s.bytes, s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.buf[b], FS3D_STONE, pb, s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.buf[b] + pb * ((size_t)s.nzl + 1), FS3D_STONE, pb, s.s_main));
+    }
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    return FS3D_OK;
+}
+
+static void free_slab(Slab &s) {
+    cudaSetDevice(s.device);
+    if (s.s_main) cudaStreamSynchronize(s.s_main);
+    if (s.s_comm) cudaStreamSynchronize(s.s_comm);
+    for (int b = 0; b < 2; ++b) if (s.buf[b]) cudaFree(s.buf[b]);
+    if (s.d_scratch) cudaFree(s.d_scratch);
+    if (s.d_img) cudaFree(s.d_img);
+    if (s.d_palette) cudaFree(s.d_palette);
+    if (s.d_skip) cudaFree(s.d_skip);
+    if (s.d_last_active) cudaFree(s.d_last_active);
+    if (s.d_tiles_run) cudaFree(s.d_tiles_run);
+    cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_halo_lo, s.ev_halo_hi, s.ev_t0, s.ev_t1};
+    for (auto e : evs) if (e) cudaEventDestroy(e);
+    if (s.s_main) cudaStreamDestroy(s.s_main);
+    if (s.s_comm) cudaStreamDestroy(s.s_comm);
+    s = Slab();
+}
+
+static void default_palette(float *p) {
+    // EMPTY transparent black, SAND, WATER, STONE; the rest a grey ramp.  A host that owns the
+    // reference's colors[256] (renderer.cpp:136-393) passes it to fs3d_set_palette instead.
+    for (int i = 0; i < 256; ++i) { float g = i / 255.0f; p[4 * i] = g; p[4 * i + 1] = g; p[4 * i + 2] = g; p[4 * i + 3] = 1.0f; }
+    const float base[4][4] = {{0, 0, 0, 0}, {0.86f, 0.72f, 0.40f, 1}, {0.15f, 0.40f, 0.85f, 1}, {0.45f, 0.45f, 0.48f, 1}};
+    for (int i = 0; i < 4; ++i) for (int c = 0; c < 4; ++c) p[4 * i + c] = base[i][c];
+}
+
+static int finish_create(fs3d_world *w) {
+    const uint32_t wpr = w->desc.nx / 32;
+    w->jidx = wpr <= 32 ? 0 : (wpr <= 64 ? 1 : 2);
+    w->lpr = wpr < 32 ? wpr : 32;
+    w->groups = w->jidx == 0 ? 32 / w->lpr : 1;
+    default_palette(w->palette);
+    for (auto &s : w->slabs) { int rc = init_slab(w, s); if (rc) return rc; }
+    return FS3D_OK;
+}
+
+// ---- one step of one slab: pairs [pb, pe) --------------------------------------------------------
+struct PairLayout { uint32_t lz_first, npairs; };
+static PairLayout pair_layout(const Slab &s, uint32_t oz) {
+    PairLayout L;
+    L.lz_first = ((s.z0 & 1u) == oz) ? 1u : 0u;
+    L.npairs = (s.nzl - L.lz_first) / 2 + 1;
+    return L;
+}
+
+static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe) {
+    if (pe <= pb) return FS3D_OK;
+    const uint64_t t = w->step;
+    const uint32_t hoff = (uint32_t)((t >> 1) & 1), todd = (uint32_t)(t & 1);
+    PairLayout L = pair_layout(s, hoff);
+    StepParams p{};
+    p.src = s.buf[w->cur];
+    p.dst = s.buf[w->cur ^ 1];
+    p.nx = w->desc.nx; p.ny = w->desc.ny;
+    p.wpr = w->desc.nx / 32; p.lpr = w->lpr; p.groups = w->groups;
+    p.z0 = (int32_t)s.z0; p.nzl = s.nzl;
+    p.lz_first = L.lz_first;
+    p.pair_begin = pb; p.pair_end = pe;
+    p.nit = w->desc.ny / 2 + 1;
+    p.key_xy = step_key(w->desc.seed, t, 0);
+    p.key_zy = step_key(w->desc.seed, t, 1);
+    p.skip = nullptr; p.last_active = nullptr;
+    p.step_plus1 = (uint32_t)(t + 1);
+
+    const uint64_t npg = ((uint64_t)(pe - pb) + w->groups - 1) / w->groups;
+    const uint64_t total = npg * p.nit;
+    // enough warps to fill the machine, but never fewer than ~8 iterations per warp
+    const int bps = s.blocks_per_sm[w->jidx][hoff][todd];
+    uint64_t max_blocks = (uint64_t)s.num_sms * bps;
+    const uint64_t warps_per_block = STEP_THREADS / 32;
+    uint64_t want_warps = std::max<uint64_t>(1, total / 8);
+    uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
+    blocks = std::max<uint64_t>(blocks, 1);
+    step_fn(w->jidx, (int)hoff, (int)todd)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
+    FS3D_CUDA(cudaGetLastError());
+    w->launches++;
+    return FS3D_OK;
+}
+
+// in-process multi-slab halo exchange of the BACK buffer after the edge pairs are written
+static int exchange_halos(fs3d_world *w) {
+    const int n = (int)w->slabs.size();
+    const size_t pb = plane_bytes(w);
+    const int back = w->cur ^ 1;
+    for (int i = 0; i < n; ++i) {
+        Slab &s = w->slabs[i];
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaStreamWaitEvent(s.s_comm, s.ev_edges, 0));
+        if (i > 0) {   // my first owned plane -> lower neighbour's ghost-high
+            Slab &d = w->slabs[i - 1];
+            FS3D_CUDA(cudaStreamWaitEvent(s.s_comm, d.ev_done, 0));   // d finished reading that ghost last step
+            FS3D_CUDA(cudaMemcpyPeerAsync(d.buf[back] + pb * ((size_t)d.nzl + 1), d.device,
+                                          s.buf[back] + pb, s.device, pb, s.s_comm));
+            FS3D_CUDA(cudaEventRecord(d.ev_halo_hi, s.s_comm));
+        }
+        if (i + 1 < n) {   // my last owned plane -> upper neighbour's ghost-low
+            Slab &d = w->slabs[i + 1];
+            FS3D_CUDA(cudaStreamWaitEvent(s.s_comm, d.ev_done, 0));
+            FS3D_CUDA(cudaMemcpyPeerAsync(d.buf[back], d.device, s.buf[back] + pb * (size_t)s.nzl, s.device, pb, s.s_comm));
+            FS3D_CUDA(cudaEventRecord(d.ev_halo_lo, s.s_comm));
+        }
+    }
+    return FS3D_OK;
+}
+
+static int step_once(fs3d_world *w) {
+    const int n = (int)w->slabs.size();
+    const uint32_t hoff = (uint32_t)((w->step >> 1) & 1);
+    if (n == 1) {
+        Slab &s = w->slabs[0];
+        FS3D_CUDA(cudaSetDevice(s.device));
+        PairLayout L = pair_layout(s, hoff);
+        int rc = launch_pairs(w, s, 0, L.npairs);
+        if (rc) return rc;
+    } else {
+        // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
+        for (auto &s : w->slabs) {
+            FS3D_CUDA(cudaSetDevice(s.device));
+            // ghosts of the front buffer must have arrived (written during the previous step)
+            if (w->halo_pending) {
+                FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_halo_lo, 0));
+                FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_halo_hi, 0));
+            }
+            PairLayout L = pair_layout(s, hoff);
+            int rc = launch_pairs(w, s, 0, 1);
+            if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs);
+            if (rc) return rc;
+            FS3D_CUDA(cudaEventRecord(s.ev_edges, s.s_main));
+        }
+        int rc = exchange_halos(w);
+        if (rc) return rc;
+        for (auto &s : w->slabs) {
+            FS3D_CUDA(cudaSetDevice(s.device));
+            PairLayout L = pair_layout(s, hoff);
+            if (L.npairs > 2) { rc = launch_pairs(w, s, 1, L.npairs - 1); if (rc) return rc; }
+            FS3D_CUDA(cudaEventRecord(s.ev_done, s.s_main));
+        }
+        w->halo_pending = true;
+    }
+    w->cur ^= 1;
+    w->step++;
+    return FS3D_OK;
+}
+
+// After the front buffer was rewritten by upload/generate/set_cell: refresh ghost planes between
+// in-process slabs (and leave STONE at the global boundary).
+static int refresh_ghosts(fs3d_world *w) {
+    const int n = (int)w->slabs.size();
+    if (n <= 1 || w->external) return FS3D_OK;
+    const size_t pb = plane_bytes(w);
+    for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); FS3D_CUDA(cudaStreamSynchronize(s.s_main)); FS3D_CUDA(cudaStreamSynchronize(s.s_comm)); }
+    for (int i = 0; i < n; ++i) {
+        Slab &s = w->slabs[i];
+        FS3D_CUDA(cudaSetDevice(s.device));
+        if (i > 0) {
+            Slab &d = w->slabs[i - 1];
+            FS3D_CUDA(cudaMemcpyPeerAsync(d.buf[w->cur] + pb * ((size_t)d.nzl + 1), d.device, s.buf[w->cur] + pb, s.device, pb, s.s_main));
+        }
+        if (i + 1 < n) {
+            Slab &d = w->slabs[i + 1];
+            FS3D_CUDA(cudaMemcpyPeerAsync(d.buf[w->cur], d.device, s.buf[w->cur] + pb * (size_t)s.nzl, s.device, pb, s.s_main));
+        }
+    }
+    for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); FS3D_CUDA(cudaStreamSynchronize(s.s_main)); }
+    w->halo_pending = false;
+    return FS3D_OK;
+}
+
+static int sync_all(fs3d_world *w) {
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_comm));
+    }
+    return FS3D_OK;
+}
+
+static Slab *slab_of_z(fs3d_world *w, uint32_t z) {
+    for (auto &s : w->slabs) if (z >= s.z0 && z < s.z0 + s.nzl) return &s;
+    return nullptr;
+}
+
+static unsigned grid_for(uint64_t n, const Slab &s) {
+    uint64_t b = (n + 255) / 256;
+    uint64_t cap = (uint64_t)s.num_sms * 16;
+    return (unsigned)std::max<uint64_t>(1, std::min(b, cap));
+}
+
+// ---- raymarch host side ----------------------------------------------------------------------------
+int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode,
+                   uint8_t *host_rgba8, float *host_depth) {
+    if ((int)w->slabs.size() > RM_MAX_SLABS) return fail(FS3D_ERR_UNSUPPORTED, "too many slabs for raymarch");
+    if ((mode & 15u) > FS3D_RM_VOXELS) return fail(FS3D_ERR_INVALID_ARG, "unknown raymarch mode");
+    Slab &s0 = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s0.device));
+    // device 0 of the world reads every slab (peer access over NVLink for in-process multi-GPU)
+    for (size_t i = 1; i < w->slabs.size(); ++i) {
+        if (w->slabs[i].device == s0.device) continue;
+        int can = 0;
+        FS3D_CUDA(cudaDeviceCanAccessPeer(&can, s0.device, w->slabs[i].device));
+        if (!can) return fail(FS3D_ERR_UNSUPPORTED, "raymarch needs peer access from the first slab's device");
+        cudaError_t e = cudaDeviceEnablePeerAccess(w->slabs[i].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FS3D_CUDA(e);
+        cudaGetLastError();
+    }
+    const size_t npix = (size_t)width * height;
+    const size_t need = npix * 4 + npix * sizeof(float) + 256 * sizeof(float);
+    if (s0.img_bytes < need) {
+        if (s0.d_img) cudaFree(s0.d_img);
+        s0.d_img = nullptr; s0.img_bytes = 0;
+        FS3D_CUDA(cudaMalloc(&s0.d_img, need));
+        s0.img_bytes = need;
+    }
+    float *d_depth = reinterpret_cast<float *>(s0.d_img + npix * 4);
+    float *d_thr = d_depth + npix;
+    if (w->palette_dirty) {
+        FS3D_CUDA(cudaMemcpyAsync(s0.d_palette, w->palette, sizeof(w->palette), cudaMemcpyHostToDevice, s0.s_main));
+        w->palette_dirty = false;
+    }
+    RMParams p{};
+    p.ox = cam->pos[0]; p.oy = cam->pos[1]; p.oz = cam->pos[2];
+    const double yaw = (double)cam->yaw_deg * 3.14159265358979323846 / 180.0;
+    p.cs = cam->yaw_deg == 0.0f ? 1.0f : (float)std::cos(yaw);
+    p.sn = cam->yaw_deg == 0.0f ? 0.0f : (float)std::sin(yaw);
+    p.aspect = cam->aspect;
+    p.W = width; p.H = height; p.mode = mode;
+    p.nx = w->desc.nx; p.ny = w->desc.ny; p.nz = w->desc.nz;
+    const uint32_t nmax = std::max(p.nx, std::max(p.ny, p.nz));
+    p.h = 1.0f / (float)nmax;
+    p.ex = (float)p.nx * p.h * 0.5f; p.ey = (float)p.ny * p.h * 0.5f; p.ez = (float)p.nz * p.h * 0.5f;
+    p.nslabs = (int)w->slabs.size();
+    for (int i = 0; i < p.nslabs; ++i) {
+        p.slab_ptr[i] = owned_ptr(w, w->slabs[i], w->cur);
+        p.slab_z0[i] = w->slabs[i].z0;
+        p.slab_z1[i] = w->slabs[i].z0 + w->slabs[i].nzl;
+    }
+    p.palette = s0.d_palette;
+    p.srgb_thr = nullptr;
+    if (mode & FS3D_RM_SRGB) {
+        float thr[256];
+        srgb_thresholds(thr);
+        thr[255] = INFINITY;
+        FS3D_CUDA(cudaMemcpyAsync(d_thr, thr, sizeof(thr), cudaMemcpyHostToDevice, s0.s_main));
+        p.srgb_thr = d_thr;
+    }
+    p.img = s0.d_img;
+    p.depth = d_depth;
+    dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
+    raymarch_kernel<<<grd, blk, 0, s0.s_main>>>(p);
+    FS3D_CUDA(cudaGetLastError());
+    w->launches++;
+    FS3D_CUDA(cudaMemcpyAsync(host_rgba8, s0.d_img, npix * 4, cudaMemcpyDeviceToHost, s0.s_main));
+    if (host_depth) FS3D_CUDA(cudaMemcpyAsync(host_depth, d_depth, npix * sizeof(float), cudaMemcpyDeviceToHost, s0.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s0.s_main));
+    return FS3D_OK;
+}
+
+}  // namespace fs3d
+
+using namespace fs3d;
+
+// =================================================================================================
+extern "C" {
+
+const char *fs3d_last_error(void) { return g_err.c_str(); }
+int fs3d_schedule_version(void) { return FS3D_SCHEDULE_VERSION; }
+
+int fs3d_create(const fs3d_desc *desc, fs3d_world **out) {
+    if (!out) return fail(FS3D_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = check_dims(desc);
+    if (rc) return rc;
+    int ndev = 0;
+    FS3D_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(FS3D_ERR_CUDA, "no CUDA device (libfs3d has no CPU fallback)");
+    int n = desc->n_gpus <= 0 ? 1 : desc->n_gpus;
+    if ((uint32_t)n > desc->nz) return fail(FS3D_ERR_BAD_DIMS, "more slabs than z-planes");
+    fs3d_world *w = new (std::nothrow) fs3d_world();
+    if (!w) return fail(FS3D_ERR_OOM, "host allocation failed");
+    w->desc = *desc;
+    w->desc.n_gpus = n;
+    w->devices.resize(n);
+    int curdev = 0;
+    cudaGetDevice(&curdev);
+    for (int i = 0; i < n; ++i) {
+        w->devices[i] = desc->devices ? desc->devices[i] : (desc->n_gpus <= 1 ? curdev : i);
+        if (w->devices[i] < 0 || w->devices[i] >= ndev) { delete w; return fail(FS3D_ERR_INVALID_ARG, "device ordinal out of range"); }
+    }
+    w->desc.devices = w->devices.data();
+    w->slabs.resize(n);
+    // contiguous slabs with even boundaries where possible (keeps ZY pairs inside slabs on oz = 0 steps)
+    uint32_t zb = 0;
+    for (int i = 0; i < n; ++i) {
+        uint64_t ze = (uint64_t)desc->nz * (i + 1) / n;
+        if (i + 1 < n && (ze & 1) && ze + 1 < desc->nz) ze += 1;
+        if (ze <= zb) ze = zb + 1;
+        if (i + 1 == n) ze = desc->nz;
+        w->slabs[i].device = w->devices[i];
+        w->slabs[i].z0 = zb;
+        w->slabs[i].nzl = (uint32_t)ze - zb;
+        zb = (uint32_t)ze;
+    }
+    if (n > 1) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                if (i == j || std::abs(i - j) != 1) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, w->devices[i], w->devices[j]);
+                if (can) { cudaSetDevice(w->devices[i]); cudaError_t e = cudaDeviceEnablePeerAccess(w->devices[j], 0); if (e != cudaSuccess) cudaGetLastError(); }
+            }
+    }
+    rc = finish_create(w);
+    if (rc) { std::string keep = g_err; fs3d_destroy(w); g_err = keep; return rc; }
+    *out = w;
+    return FS3D_OK;
+}
+
+int fs3d_create_slab(const fs3d_desc *desc, uint32_t z_begin, uint32_t z_end, fs3d_world **out) {
+    if (!out) return fail(FS3D_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int rc = check_dims(desc);
+    if (rc) return rc;
+    if (z_begin >= z_end || z_end > desc->nz) return fail(FS3D_ERR_OUT_OF_RANGE, "slab [z_begin, z_end) outside the grid");
+    int ndev = 0;
+    FS3D_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(FS3D_ERR_CUDA, "no CUDA device (libfs3d has no CPU fallback)");
+    fs3d_world *w = new (std::nothrow) fs3d_world();
+    if (!w) return fail(FS3D_ERR_OOM, "host allocation failed");
+    w->desc = *desc;
+    w->desc.n_gpus = 1;
+    int curdev = 0;
+    cudaGetDevice(&curdev);
+    w->devices.assign(1, curdev);
+    w->desc.devices = w->devices.data();
+    w->external = true;
+    w->slabs.resize(1);
+    w->slabs[0].device = curdev;
+    w->slabs[0].z0 = z_begin;
+    w->slabs[0].nzl = z_end - z_begin;
+    rc = finish_create(w);
+    if (rc) { std::string keep = g_err; fs3d_destroy(w); g_err = keep; return rc; }
+    *out = w;
+    return FS3D_OK;
+}
+
+void fs3d_destroy(fs3d_world *w) {
+    if (!w) return;
+    for (auto &s : w->slabs) free_slab(s);
+    delete w;
+}
+
+int fs3d_sync(fs3d_world *w) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    return sync_all(w);
+}
+
+int fs3d_step_index(fs3d_world *w, uint64_t *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    *out = w->step;
+    return FS3D_OK;
+}
+
+int fs3d_step(fs3d_world *w, uint32_t n_steps) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (w->external && w->desc.nz != w->slabs[0].nzl)
+        return fail(FS3D_ERR_UNSUPPORTED, "slab worlds step through fs3d_slab_step_* with a caller-driven halo exchange");
+    for (uint32_t i = 0; i < n_steps; ++i) { int rc = step_once(w); if (rc) return rc; }
+    return FS3D_OK;
+}
+
+int fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kernel_launches) {
+    if (!w || !ms) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    const uint64_t l0 = w->launches;
+    for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); FS3D_CUDA(cudaEventRecord(s.ev_t0, s.s_main)); }
+    rc = fs3d_step(w, n_steps);
+    if (rc) return rc;
+    for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); FS3D_CUDA(cudaEventRecord(s.ev_t1, s.s_main)); }
+    rc = sync_all(w);
+    if (rc) return rc;
+    float best = 0.f;
+    for (auto &s : w->slabs) {
+        float t = 0.f;
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaEventElapsedTime(&t, s.ev_t0, s.ev_t1));
+        best = std::max(best, t);
+    }
+    *ms = best;
+    if (kernel_launches) *kernel_launches = w->launches - l0;
+    return FS3D_OK;
+}
+
+// ---- cell access -----------------------------------------------------------------------------------
+static int check_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (x >= w->desc.nx || y >= w->desc.ny || z >= w->desc.nz) return fail(FS3D_ERR_OUT_OF_RANGE, "cell outside the grid");
+    return FS3D_OK;
+}
+
+int fs3d_set_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t m) {
+    int rc = check_cell(w, x, y, z);
+    if (rc) return rc;
+    if (m > FS3D_STONE) return fail(FS3D_ERR_BAD_MATERIAL, "material codes 4-255 are reserved");
+    Slab *s = slab_of_z(w, z);
+    if (!s) return FS3D_OK;   // not in this rank's slab: nothing to do
+    rc = sync_all(w);
+    if (rc) return rc;
+    FS3D_CUDA(cudaSetDevice(s->device));
+    uint8_t *p = owned_ptr(w, *s, w->cur) + x + (size_t)w->desc.nx * (y + (size_t)w->desc.ny * (z - s->z0));
+    FS3D_CUDA(cudaMemcpy(p, &m, 1, cudaMemcpyHostToDevice));
+    if (z == s->z0 || z == s->z0 + s->nzl - 1) return refresh_ghosts(w);
+    return FS3D_OK;
+}
+
+int fs3d_get_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t *m) {
+    int rc = check_cell(w, x, y, z);
+    if (rc) return rc;
+    if (!m) return fail(FS3D_ERR_INVALID_ARG, "m is NULL");
+    Slab *s = slab_of_z(w, z);
+    if (!s) return fail(FS3D_ERR_OUT_OF_RANGE, "cell is not in this rank's slab");
+    rc = sync_all(w);
+    if (rc) return rc;
+    FS3D_CUDA(cudaSetDevice(s->device));
+    const uint8_t *p = owned_ptr(w, *s, w->cur) + x + (size_t)w->desc.nx * (y + (size_t)w->desc.ny * (z - s->z0));
+    FS3D_CUDA(cudaMemcpy(m, p, 1, cudaMemcpyDeviceToHost));
+    return FS3D_OK;
+}
+
+int fs3d_fill_box(fs3d_world *w, const uint32_t lo[3], const uint32_t hi[3], uint8_t m) {
+    if (!w || !lo || !hi) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (m > FS3D_STONE) return fail(FS3D_ERR_BAD_MATERIAL, "material codes 4-255 are reserved");
+    if (hi[0] > w->desc.nx || hi[1] > w->desc.ny || hi[2] > w->desc.nz || lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2])
+        return fail(FS3D_ERR_OUT_OF_RANGE, "box outside the grid");
+    if (lo[0] == hi[0] || lo[1] == hi[1] || lo[2] == hi[2]) return FS3D_OK;
+    int rc = sync_all(w);
+    if (rc) return rc;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        uint64_t n = (uint64_t)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+        fill_box_kernel<<<grid_for(n, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), w->desc.nx, w->desc.ny, s.z0, s.nzl,
+                                                               lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], m);
+        FS3D_CUDA(cudaGetLastError());
+    }
+    rc = sync_all(w);
+    if (rc) return rc;
+    return refresh_ghosts(w);
+}
+
+int fs3d_generate(fs3d_world *w, int scene_id, uint64_t seed) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (scene_id < 0 || scene_id > FS3D_SCENE_MIXED_NOISE) return fail(FS3D_ERR_INVALID_ARG, "unknown scene id");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    const uint32_t key = step_key(seed, 0, 7);
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        uint64_t nvec = (uint64_t)w->desc.nx / 16 * w->desc.ny * s.nzl;
+        generate_kernel<<<grid_for(nvec, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), w->desc.nx, w->desc.ny, w->desc.nz,
+                                                                  s.z0, s.nzl, scene_id, key);
+        FS3D_CUDA(cudaGetLastError());
+    }
+    rc = sync_all(w);
+    if (rc) return rc;
+    return refresh_ghosts(w);
+}
+
+int fs3d_upload(fs3d_world *w, const uint8_t *host) {
+    if (!w || !host) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    const size_t pb = plane_bytes(w);
+    const uint32_t zbase = w->slabs[0].z0;
+    // stage into the BACK buffer, validate there, and only then flip: a rejected upload leaves
+    // the world untouched
+    const int back = w->cur ^ 1;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaMemcpyAsync(owned_ptr(w, s, back), host + pb * (size_t)(s.z0 - zbase), pb * s.nzl, cudaMemcpyHostToDevice, s.s_main));
+        uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
+        FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
+        uint64_t n16 = pb * s.nzl / 16;
+        validate_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, back), n16, flag);
+        FS3D_CUDA(cudaGetLastError());
+    }
+    bool bad = false;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        uint32_t f = 0;
+        FS3D_CUDA(cudaMemcpyAsync(&f, reinterpret_cast<uint32_t *>(s.d_scratch + 258), sizeof(uint32_t), cudaMemcpyDeviceToHost, s.s_main));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+        bad = bad || f != 0;
+    }
+    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, "upload contains material codes 4-255 (reserved)");
+    w->cur = back;
+    return refresh_ghosts(w);
+}
+
+int fs3d_download(fs3d_world *w, uint8_t *host) {
+    if (!w || !host) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    const size_t pb = plane_bytes(w);
+    const uint32_t zbase = w->slabs[0].z0;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaMemcpyAsync(host + pb * (size_t)(s.z0 - zbase), owned_ptr(w, s, w->cur), pb * s.nzl, cudaMemcpyDeviceToHost, s.s_main));
+    }
+    return sync_all(w);
+}
+
+// ---- reductions --------------------------------------------------------------------------------------
+int fs3d_histogram(fs3d_world *w, uint64_t counts[256]) {
+    if (!w || !counts) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    std::memset(counts, 0, 256 * sizeof(uint64_t));
+    const size_t pb = plane_bytes(w);
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaMemsetAsync(s.d_scratch, 0, 256 * sizeof(unsigned long long), s.s_main));
+        uint64_t n16 = pb * s.nzl / 16;
+        histogram_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), n16, s.d_scratch);
+        FS3D_CUDA(cudaGetLastError());
+        unsigned long long h[256];
+        FS3D_CUDA(cudaMemcpyAsync(h, s.d_scratch, sizeof(h), cudaMemcpyDeviceToHost, s.s_main));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+        for (int i = 0; i < 256; ++i) counts[i] += h[i];
+    }
+    return FS3D_OK;
+}
+
+int fs3d_digest(fs3d_world *w, uint64_t *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    const size_t pb = plane_bytes(w);
+    uint64_t sum = 0;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        unsigned long long *d = s.d_scratch + 256;
+        FS3D_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s.s_main));
+        uint64_t n16 = pb * s.nzl / 16;
+        digest_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), n16, (uint64_t)s.z0 * pb, d);
+        FS3D_CUDA(cudaGetLastError());
+        unsigned long long h = 0;
+        FS3D_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s.s_main));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+        sum += h;
+    }
+    *out = sum;
+    return FS3D_OK;
+}
+
+int fs3d_activity(fs3d_world *w, uint64_t *tiles_run, uint64_t *tiles_total) {
+    if (!w || !tiles_run || !tiles_total) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    *tiles_run = 0; *tiles_total = 0;
+    return FS3D_OK;
+}
+
+// ---- renderer hand-off -----------------------------------------------------------------------------
+int fs3d_num_slabs(fs3d_world *w, int32_t *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    *out = (int32_t)w->slabs.size();
+    return FS3D_OK;
+}
+
+int fs3d_volume_view(fs3d_world *w, int32_t slab, fs3d_view *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (slab < 0 || slab >= (int32_t)w->slabs.size()) return fail(FS3D_ERR_OUT_OF_RANGE, "slab index out of range");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    Slab &s = w->slabs[slab];
+    out->dev_ptr = owned_ptr(w, s, w->cur);
+    out->device = s.device;
+    out->nx = w->desc.nx; out->ny = w->desc.ny;
+    out->z0 = s.z0; out->z1 = s.z0 + s.nzl;
+    out->pitch_y = w->desc.nx;
+    out->pitch_z = plane_bytes(w);
+    out->step = w->step;
+    return FS3D_OK;
+}
+
+int fs3d_set_palette(fs3d_world *w, const float *rgba256x4) {
+    if (!w || !rgba256x4) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    std::memcpy(w->palette, rgba256x4, sizeof(w->palette));
+    w->palette_dirty = true;
+    return FS3D_OK;
+}
+
+int fs3d_raymarch(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode, uint8_t *host_rgba8) {
+    if (!w || !cam || !host_rgba8) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(FS3D_ERR_INVALID_ARG, "bad image size");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    return raymarch_world(w, cam, width, height, mode, host_rgba8, nullptr);
+}
+
+int fs3d_raymarch_depth(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode,
+                        uint8_t *host_rgba8, float *host_depth) {
+    if (!w || !cam || !host_rgba8 || !host_depth) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(FS3D_ERR_INVALID_ARG, "bad image size");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    return raymarch_world(w, cam, width, height, mode, host_rgba8, host_depth);
+}
+
+// ---- one-process-per-GPU slab protocol -----------------------------------------------------------
+int fs3d_slab_halo(fs3d_world *w, int back, fs3d_halo *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (w->slabs.size() != 1) return fail(FS3D_ERR_UNSUPPORTED, "fs3d_slab_halo needs a world made by fs3d_create_slab");
+    Slab &s = w->slabs[0];
+    const size_t pb = plane_bytes(w);
+    uint8_t *b = s.buf[back ? (w->cur ^ 1) : w->cur];
+    out->recv_lo = b;
+    out->send_lo = b + pb;
+    out->send_hi = b + pb * (size_t)s.nzl;
+    out->recv_hi = b + pb * ((size_t)s.nzl + 1);
+    out->plane_bytes = pb;
+    out->stream = (void *)s.s_main;
+    return FS3D_OK;
+}
+
+int fs3d_slab_step_edges(fs3d_world *w) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (w->slabs.size() != 1) return fail(FS3D_ERR_UNSUPPORTED, "needs a single-slab world");
+    if (w->edges_phase != 0) return fail(FS3D_ERR_INVALID_ARG, "fs3d_slab_step_edges called twice without finish");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    PairLayout L = pair_layout(s, (uint32_t)((w->step >> 1) & 1));
+    int rc = launch_pairs(w, s, 0, 1);
+    if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs);
+    if (rc) return rc;
+    w->edges_phase = 1;
+    return FS3D_OK;
+}
+
+int fs3d_slab_step_interior(fs3d_world *w) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (w->slabs.size() != 1) return fail(FS3D_ERR_UNSUPPORTED, "needs a single-slab world");
+    if (w->edges_phase != 1) return fail(FS3D_ERR_INVALID_ARG, "call fs3d_slab_step_edges first");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    PairLayout L = pair_layout(s, (uint32_t)((w->step >> 1) & 1));
+    if (L.npairs > 2) { int rc = launch_pairs(w, s, 1, L.npairs - 1); if (rc) return rc; }
+    w->edges_phase = 2;
+    return FS3D_OK;
+}
+
+int fs3d_slab_step_finish(fs3d_world *w) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (w->edges_phase != 2) return fail(FS3D_ERR_INVALID_ARG, "call fs3d_slab_step_interior first");
+    w->cur ^= 1;
+    w->step++;
+    w->edges_phase = 0;
+    return FS3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""SlabWorld — one process per GPU: z-slab decomposition with a one-plane halo exchange per step
+over torch.distributed (NCCL over NVLink on the GPUs; gloo in the CPU tests of this host logic).
+
+No reference counterpart: the reference is single-GPU, single-threaded and has no distributed
+backend (SURVEY.md §5 "Distributed communication backend: None").  SURVEY.md §8(e) is the spec:
+each rank owns a contiguous z-slab plus one ghost plane each side; per step the two edge planes
+are computed first, sent to the z-neighbours while the interior is computed, and both sides of a
+boundary-crossing ZY block are evaluated redundantly from identical data (global coordinates and
+the counter hash make them agree), so no move message is needed.
+
+The compute engine is pluggable so that the partition / exchange / reduction logic can be tested
+on CPU: CudaSlabEngine drives libfs3d through the C ABI; tests inject an oracle-backed engine.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab_bounds(nz, world_size):
+    """Contiguous z-ranges, boundaries on even planes where possible (the same rule as fs3d_create)."""
+    bounds = []
+    zb = 0
+    for i in range(world_size):
+        ze = nz * (i + 1) // world_size
+        if i + 1 < world_size and (ze & 1) and ze + 1 < nz:
+            ze += 1
+        if ze <= zb:
+            ze = zb + 1
+        if i + 1 == world_size:
+            ze = nz
+        bounds.append((zb, ze))
+        zb = ze
+    if bounds[-1][0] >= bounds[-1][1]:
+        raise ValueError("more ranks than z-planes")
+    return bounds
+
+
+class _DevPtr:
+    """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class CudaSlabEngine:
+    """libfs3d slab world on the current CUDA device (fs3d_create_slab + fs3d_slab_* protocol)."""
+
+    def __init__(self, nx, ny, nz, seed, z_begin, z_end, device, flags=0):
+        from .world import VoxelWorld
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.world = VoxelWorld(nx, ny, nz, seed=seed, flags=flags, slab=(z_begin, z_end))
+        self._views = {}
+        h = self.world.slab_halo(0)
+        self.stream = torch.cuda.ExternalStream(h.stream, device=self.device)
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.edges_done = torch.cuda.Event()
+
+    def halo_tensors(self, back):
+        h = self.world.slab_halo(back)
+        key = (h.send_lo, h.send_hi, h.recv_lo, h.recv_hi)
+        if key not in self._views:
+            n = h.plane_bytes
+            self._views[key] = tuple(torch.as_tensor(_DevPtr(p, n), device=self.device)
+                                     for p in (h.send_lo, h.send_hi, h.recv_lo, h.recv_hi))
+        return self._views[key]
+
+    # stream hooks: the exchange runs on comm_stream, ordered after the edge kernels, and the next
+    # step's kernels are ordered after it
+    def before_exchange(self, after_edges):
+        if after_edges:
+            self.comm_stream.wait_event(self.edges_done)   # not the interior kernel enqueued behind it
+        else:
+            self.comm_stream.wait_stream(self.stream)
+        return torch.cuda.stream(self.comm_stream)
+
+    def after_exchange(self):
+        self.stream.wait_stream(self.comm_stream)
+
+    def step_edges(self):
+        self.world.slab_step_edges()
+        self.edges_done.record(self.stream)
+
+    def step_interior(self):
+        self.world.slab_step_interior()
+
+    def step_finish(self):
+        self.world.slab_step_finish()
+
+    def sync(self):
+        self.world.sync()
+        self.comm_stream.synchronize()
+
+    def generate(self, scene, seed):
+        self.world.generate(scene, seed)
+
+    def upload(self, a):
+        self.world.upload(a)
+
+    def download(self):
+        return self.world.download()
+
+    def digest(self):
+        return self.world.digest()
+
+    def histogram(self):
+        return self.world.histogram()
+
+    def reduce_device(self):
+        return self.device
+
+    def close(self):
+        self.world.close()
+
+
+class SlabWorld:
+    """The rank-local piece of a global nx×ny×nz world, stepped in lock-step with the other ranks."""
+
+    def __init__(self, nx, ny, nz, seed=1, flags=0, engine_factory=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.nx, self.ny, self.nz, self.seed = nx, ny, nz, seed
+        self.bounds = slab_bounds(nz, self.world_size)
+        self.z_begin, self.z_end = self.bounds[self.rank]
+        if engine_factory is None:
+            dev = torch.cuda.current_device()
+            self.engine = CudaSlabEngine(nx, ny, nz, seed, self.z_begin, self.z_end, dev, flags)
+        else:
+            self.engine = engine_factory(nx, ny, nz, seed, self.z_begin, self.z_end)
+        self.step_index = 0
+        self.exchanges = 0
+
+    # ---- halo exchange of one buffer (back = the buffer the current step is writing) ----
+    def _exchange(self, back):
+        if self.world_size == 1:
+            return
+        send_lo, send_hi, recv_lo, recv_hi = self.engine.halo_tensors(back)
+        ops = []
+        lo, hi = self.rank - 1, self.rank + 1
+        # post receives first; the order of sends/recvs is the same on every rank pair
+        if lo >= 0:
+            ops.append(dist.P2POp(dist.irecv, recv_lo, lo, self.group))
+            ops.append(dist.P2POp(dist.isend, send_lo, lo, self.group))
+        if hi < self.world_size:
+            ops.append(dist.P2POp(dist.isend, send_hi, hi, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, hi, self.group))
+        with self.engine.before_exchange(after_edges=bool(back)):
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.engine.after_exchange()
+        self.exchanges += 1
+
+    def refresh_halos(self):
+        """After generate/upload/set_cell: make the front buffer's ghost planes current."""
+        self._exchange(back=0)
+
+    def generate(self, scene, seed=None):
+        self.engine.generate(scene, self.seed if seed is None else seed)
+        self.refresh_halos()
+
+    def upload(self, local_planes):
+        self.engine.upload(local_planes)
+        self.refresh_halos()
+
+    def download(self):
+        return self.engine.download()
+
+    def step(self, n=1):
+        for _ in range(n):
+            self.engine.step_edges()        # the two edge planes of the back buffer are final after this
+            self.engine.step_interior()     # enqueue first so it overlaps with the exchange below
+            self._exchange(back=1)
+            self.engine.step_finish()
+            self.step_index += 1
+
+    def sync(self):
+        self.engine.sync()
+
+    # ---- global reductions ----
+    def _allreduce_u64(self, arr):
+        if self.world_size == 1:
+            return arr
+        # split into 32-bit halves so that a float-free integer SUM cannot overflow int64
+        a = np.asarray(arr, dtype=np.uint64)
+        parts = np.stack([(a & np.uint64(0xFFFFFFFF)).astype(np.int64), (a >> np.uint64(32)).astype(np.int64)])
+        t = torch.from_numpy(parts).to(self.engine.reduce_device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        p = t.cpu().numpy().astype(np.uint64)
+        return (p[0] + (p[1] << np.uint64(32))).astype(np.uint64)   # wraps mod 2^64, like the digest sum
+
+    def digest(self):
+        return int(self._allreduce_u64(np.array([self.engine.digest()], dtype=np.uint64))[0])
+
+    def histogram(self):
+        return self._allreduce_u64(self.engine.histogram())
+
+    def gather(self):
+        """Whole grid on every rank (tests / small worlds only)."""
+        local = torch.from_numpy(self.download())
+        if self.world_size == 1:
+            return local.numpy()
+        outs = [None] * self.world_size
+        dist.all_gather_object(outs, local.numpy(), group=self.group)
+        return np.concatenate(outs, axis=0)
+
+    def close(self):
+        self.engine.close()

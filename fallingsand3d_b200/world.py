@@ -1,0 +1,197 @@
+"""VoxelWorld — host-side mirror of the voxel-world interface (create, set/get cell, step,
+hand-off to the ray-marcher) over the C ABI in include/fs3d.h.
+
+The reference has no such interface to copy names from; this class is what
+its frame loop would hold (/root/reference/src/engine/engine.cpp:59-70) and it raises
+RuntimeError("ERROR: ...") on failure the way util::displayError logs then throws
+(/root/reference/src/util/debug.cpp:23-27).
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _lib
+
+EMPTY, SAND, WATER, STONE = 0, 1, 2, 3
+SCENE_EMPTY, SCENE_SAND_BLOCK, SCENE_MIXED, SCENE_RANDOM, SCENE_MIXED_NOISE = 0, 1, 2, 3, 4
+FLAG_SKIP_SETTLED = 1
+RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
+
+ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
+               -6: "OOM", -7: "UNSUPPORTED"}
+
+
+class Fs3dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ERROR: fs3d {ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        msg = _lib.load().fs3d_last_error().decode("utf-8", "replace")
+        print(f"ERROR: {msg}", file=sys.stderr)   # debug.cpp:16 prints before debug.cpp:26 throws
+        raise Fs3dError(rc, msg)
+
+
+class VoxelWorld:
+    """A double-buffered uint8 voxel grid on one or more B200s.
+
+    VoxelWorld(nx, ny, nz, seed=1, n_gpus=1, devices=None, flags=0) owns the whole grid in this
+    process (n_gpus z-slabs with in-library P2P halo exchange).
+    VoxelWorld(..., slab=(z_begin, z_end)) owns one rank's slab on the current CUDA device; the
+    caller drives the halo exchange (see slab.SlabWorld).
+    """
+
+    def __init__(self, nx, ny, nz, seed=1, n_gpus=1, devices=None, flags=0, slab=None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.nx, self.ny, self.nz, self.seed = int(nx), int(ny), int(nz), int(seed)
+        dev_arr = None
+        if devices is not None:
+            dev_arr = (C.c_int32 * len(devices))(*devices)
+            n_gpus = len(devices)
+        d = _lib.Desc(self.nx, self.ny, self.nz, self.seed, int(n_gpus),
+                      C.cast(dev_arr, C.POINTER(C.c_int32)) if dev_arr is not None else None, int(flags))
+        if slab is None:
+            self.z_begin, self.z_end = 0, self.nz
+            _check(self._lib.fs3d_create(C.byref(d), C.byref(self._h)))
+        else:
+            self.z_begin, self.z_end = int(slab[0]), int(slab[1])
+            _check(self._lib.fs3d_create_slab(C.byref(d), self.z_begin, self.z_end, C.byref(self._h)))
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.fs3d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def shape(self):
+        """(nz_held, ny, nx) — numpy order of upload()/download() arrays."""
+        return (self.z_end - self.z_begin, self.ny, self.nx)
+
+    # ---- cells ----
+    def set_cell(self, x, y, z, m):
+        _check(self._lib.fs3d_set_cell(self._h, x, y, z, m))
+
+    def get_cell(self, x, y, z):
+        out = C.c_uint8()
+        _check(self._lib.fs3d_get_cell(self._h, x, y, z, C.byref(out)))
+        return out.value
+
+    def fill_box(self, lo, hi, m):
+        a = (C.c_uint32 * 3)(*lo)
+        b = (C.c_uint32 * 3)(*hi)
+        _check(self._lib.fs3d_fill_box(self._h, a, b, m))
+
+    def generate(self, scene_id, seed=None):
+        _check(self._lib.fs3d_generate(self._h, int(scene_id), self.seed if seed is None else int(seed)))
+
+    def upload(self, grid):
+        g = np.ascontiguousarray(grid, dtype=np.uint8)
+        if g.shape != self.shape:
+            raise ValueError(f"expected array of shape {self.shape} (z, y, x), got {g.shape}")
+        _check(self._lib.fs3d_upload(self._h, g.ctypes.data_as(C.c_void_p)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == self.shape
+        _check(self._lib.fs3d_download(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ---- stepping ----
+    def step(self, n=1):
+        _check(self._lib.fs3d_step(self._h, int(n)))
+
+    def sync(self):
+        _check(self._lib.fs3d_sync(self._h))
+
+    @property
+    def step_index(self):
+        out = C.c_uint64()
+        _check(self._lib.fs3d_step_index(self._h, C.byref(out)))
+        return out.value
+
+    def step_timed(self, n=1):
+        """Runs n steps; returns (device milliseconds from CUDA events on the step stream, kernels launched)."""
+        ms = C.c_float()
+        nl = C.c_uint64()
+        _check(self._lib.fs3d_step_timed(self._h, int(n), C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    # ---- reductions ----
+    def histogram(self):
+        h = (C.c_uint64 * 256)()
+        _check(self._lib.fs3d_histogram(self._h, h))
+        return np.frombuffer(h, dtype=np.uint64).copy()
+
+    def digest(self):
+        out = C.c_uint64()
+        _check(self._lib.fs3d_digest(self._h, C.byref(out)))
+        return out.value
+
+    def activity(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self._lib.fs3d_activity(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- renderer hand-off ----
+    @property
+    def num_slabs(self):
+        out = C.c_int32()
+        _check(self._lib.fs3d_num_slabs(self._h, C.byref(out)))
+        return out.value
+
+    def volume_view(self, slab=0):
+        v = _lib.View()
+        _check(self._lib.fs3d_volume_view(self._h, slab, C.byref(v)))
+        return {k: getattr(v, k) for k, _ in _lib.View._fields_}
+
+    def set_palette(self, rgba):
+        p = np.ascontiguousarray(rgba, dtype=np.float32)
+        assert p.shape == (256, 4)
+        _check(self._lib.fs3d_set_palette(self._h, p.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def raymarch(self, pos=(0.0, 0.0, -5.0), yaw_deg=0.0, aspect=1700.0 / 900.0, width=850, height=450,
+                 mode=RM_VOXELS, with_depth=False):
+        """Offscreen image (H, W, 4) uint8; defaults are the reference camera
+        (renderer.h:148-149, window.h:41, materials.cpp:540)."""
+        cam = _lib.Camera((C.c_float * 3)(*pos), yaw_deg, aspect)
+        img = np.empty((height, width, 4), dtype=np.uint8)
+        if with_depth:
+            depth = np.empty((height, width), dtype=np.float32)
+            _check(self._lib.fs3d_raymarch_depth(self._h, C.byref(cam), width, height, mode,
+                                                 img.ctypes.data_as(C.c_void_p), depth.ctypes.data_as(C.c_void_p)))
+            return img, depth
+        _check(self._lib.fs3d_raymarch(self._h, C.byref(cam), width, height, mode, img.ctypes.data_as(C.c_void_p)))
+        return img
+
+    # ---- one-process-per-GPU slab protocol (see slab.SlabWorld) ----
+    def slab_halo(self, back):
+        h = _lib.Halo()
+        _check(self._lib.fs3d_slab_halo(self._h, int(back), C.byref(h)))
+        return h
+
+    def slab_step_edges(self):
+        _check(self._lib.fs3d_slab_step_edges(self._h))
+
+    def slab_step_interior(self):
+        _check(self._lib.fs3d_slab_step_interior(self._h))
+
+    def slab_step_finish(self):
+        _check(self._lib.fs3d_slab_step_finish(self._h))

@@ -1,0 +1,168 @@
+/*
+ * fs3d.h — C ABI of libfs3d: the B200-native voxel-world step for FallingSand3D.
+ *
+ * The reference engine (/root/reference) has no plugin/FFI boundary and, in the surveyed
+ * snapshot, no voxel world at all.  Each entry point below therefore cites
+ * the reference *seam* it plugs into rather than a function it replaces:
+ *
+ *   - frame loop, where step() is called once per frame between handleEvents() and draw():
+ *       src/engine/engine.cpp:59-70  (VulkanEngine::run)
+ *   - material binding builder, the only place a volume could be handed to a ray-march shader:
+ *       src/engine/rendering/materials.cpp:26-59 (addDataBinding/addImageBinding),
+ *       src/engine/rendering/materials.cpp:388-418 (writeBuffer/writeImage/finalize)
+ *   - full-screen ray-march camera + shading model:
+ *       shaders/fs_raymarch.vert:30-37, shaders/fs_raymarch.frag:38-81,
+ *       quad UVs src/engine/rendering/renderer.cpp:1253-1267,
+ *       camera defaults src/engine/rendering/renderer.h:148-149
+ *   - error convention (log "ERROR: ..." then throw std::runtime_error), mirrored by the C++
+ *     wrapper include/fs3d.hpp:  src/util/debug.cpp:23-27
+ *   - 256-entry colour palette indexed by uint8 material:
+ *       src/engine/rendering/renderer.cpp:136-393 (colors[], unused by the reference)
+ *
+ * Conventions: plain C types only; every function returns 0 (FS3D_OK) or a negative error code
+ * and never throws; fs3d_last_error() returns a thread-local message.  A world handle is not
+ * thread-safe (the reference is single-threaded): use one host thread per handle.  The library
+ * owns all device memory; host pointers passed in are borrowed for the duration of the call.
+ * Kernels run asynchronously on library-owned streams; fs3d_sync() blocks.
+ * There is NO CPU fallback: every call that computes fails with FS3D_ERR_CUDA without a GPU.
+ *
+ * The update rule is specified in SCHEDULE.md (schedule version FS3D_SCHEDULE_VERSION).
+ */
+#ifndef FS3D_H
+#define FS3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS3D_SCHEDULE_VERSION 1
+
+/* materials (SCHEDULE.md §1) */
+#define FS3D_EMPTY 0
+#define FS3D_SAND  1
+#define FS3D_WATER 2
+#define FS3D_STONE 3
+
+/* error codes */
+#define FS3D_OK                 0
+#define FS3D_ERR_INVALID_ARG   -1
+#define FS3D_ERR_BAD_DIMS      -2
+#define FS3D_ERR_BAD_MATERIAL  -3
+#define FS3D_ERR_OUT_OF_RANGE  -4
+#define FS3D_ERR_CUDA          -5
+#define FS3D_ERR_OOM           -6
+#define FS3D_ERR_UNSUPPORTED   -7
+
+/* fs3d_desc.flags */
+#define FS3D_FLAG_SKIP_SETTLED  1u   /* settled-tile skipping (bit-exact; SCHEDULE.md §4) */
+
+/* scene ids for fs3d_generate (SCHEDULE.md §5) */
+#define FS3D_SCENE_EMPTY        0
+#define FS3D_SCENE_SAND_BLOCK   1
+#define FS3D_SCENE_MIXED        2
+#define FS3D_SCENE_RANDOM       3
+#define FS3D_SCENE_MIXED_NOISE  4
+
+typedef struct fs3d_world fs3d_world;
+
+typedef struct {
+    uint32_t nx, ny, nz;      /* global grid; nx % 32 == 0, nx <= 4096 */
+    uint64_t seed;            /* coin seed (SCHEDULE.md §3) */
+    int32_t  n_gpus;          /* z-slabs, one per device, driven by this process; 0 or 1 = current device */
+    const int32_t *devices;   /* n_gpus CUDA device ordinals, or NULL for 0..n_gpus-1 */
+    uint32_t flags;           /* FS3D_FLAG_* */
+} fs3d_desc;
+
+/* A borrowed view of one slab of the current (front) buffer — the volume hand-off to a renderer.
+ * Valid until the next fs3d_step / upload / generate / destroy on the world. */
+typedef struct {
+    const uint8_t *dev_ptr;   /* device pointer to cell (0, 0, z0) */
+    int32_t  device;          /* CUDA ordinal that owns dev_ptr */
+    uint32_t nx, ny;
+    uint32_t z0, z1;          /* global planes [z0, z1) held by this slab */
+    uint64_t pitch_y, pitch_z;/* bytes between rows / planes */
+    uint64_t step;            /* step index the view corresponds to */
+} fs3d_view;
+
+/* Camera of shaders/fs_raymarch.{vert,frag}: origin + aspect; yaw is the engine's camRot.y
+ * (renderer.cpp:460-467), which fs_raymarch itself ignores (0 reproduces the shader). */
+typedef struct {
+    float pos[3];
+    float yaw_deg;
+    float aspect;             /* reference: 1700/900 (materials.cpp:540) */
+} fs3d_camera;
+
+/* fs3d_raymarch modes */
+#define FS3D_RM_SDF_SPHERE 0   /* fs_raymarch.frag as shipped: analytic sphere r=0.5 at origin */
+#define FS3D_RM_VOXELS     1   /* same camera/light, voxel DDA through the grid + palette */
+#define FS3D_RM_SRGB       16  /* OR-able: sRGB-encode like the reference's B8G8R8A8_SRGB swapchain */
+
+/* Device pointers for an external (one-process-per-GPU) halo exchange; see fs3d_create_slab. */
+typedef struct {
+    uint8_t *send_lo, *send_hi;  /* first / last owned plane of the buffer being exchanged */
+    uint8_t *recv_lo, *recv_hi;  /* ghost planes below / above the slab in the same buffer */
+    uint64_t plane_bytes;        /* nx * ny */
+    void    *stream;             /* cudaStream_t the step kernels run on */
+} fs3d_halo;
+
+/* ---- lifetime ---- */
+int  fs3d_create(const fs3d_desc *desc, fs3d_world **out);
+/* One rank's slab [z_begin, z_end) of a desc->nz-plane world on the CURRENT device; the caller
+ * exchanges halos (fs3d_slab_* below).  desc->n_gpus/devices are ignored. */
+int  fs3d_create_slab(const fs3d_desc *desc, uint32_t z_begin, uint32_t z_end, fs3d_world **out);
+void fs3d_destroy(fs3d_world *w);
+
+/* ---- cell access (global coordinates) ---- */
+int  fs3d_set_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t m);
+int  fs3d_get_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t *m);
+int  fs3d_fill_box(fs3d_world *w, const uint32_t lo[3], const uint32_t hi[3], uint8_t m); /* half-open */
+int  fs3d_generate(fs3d_world *w, int scene_id, uint64_t seed);
+int  fs3d_upload(fs3d_world *w, const uint8_t *host);    /* host: the planes this world holds, x fastest */
+int  fs3d_download(fs3d_world *w, uint8_t *host);
+
+/* ---- stepping ---- */
+int  fs3d_step(fs3d_world *w, uint32_t n_steps);          /* asynchronous */
+int  fs3d_sync(fs3d_world *w);
+int  fs3d_step_index(fs3d_world *w, uint64_t *out);
+/* Runs n_steps and returns the device time between CUDA events recorded on the step stream
+ * (max over slabs).  kernel_launches, if non-NULL, receives the number of kernels launched. */
+int  fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kernel_launches);
+
+/* ---- reductions (over the planes this world holds; sum across ranks yourself) ---- */
+int  fs3d_histogram(fs3d_world *w, uint64_t counts[256]);
+int  fs3d_digest(fs3d_world *w, uint64_t *out);
+/* Settled-tile statistics of the last step: tiles processed / tiles total (skipping on). */
+int  fs3d_activity(fs3d_world *w, uint64_t *tiles_run, uint64_t *tiles_total);
+
+/* ---- renderer hand-off ---- */
+int  fs3d_num_slabs(fs3d_world *w, int32_t *out);
+int  fs3d_volume_view(fs3d_world *w, int32_t slab, fs3d_view *out);
+int  fs3d_set_palette(fs3d_world *w, const float *rgba256x4);
+int  fs3d_raymarch(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height,
+                   uint32_t mode, uint8_t *host_rgba8);
+/* Same, plus the hit parameter t per pixel (+inf on a miss): ranks that each hold one slab
+ * composite their images by taking, per pixel, the colour with the smallest t. */
+int  fs3d_raymarch_depth(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height,
+                         uint32_t mode, uint8_t *host_rgba8, float *host_depth);
+
+/* ---- one-process-per-GPU slab stepping with caller-driven halo exchange ----
+ * Per step:  fs3d_slab_step_edges (writes the slab's two edge planes of the back buffer)
+ *            → caller sends send_lo/send_hi of fs3d_slab_halo(.., back=1) to its z-neighbours and
+ *              receives into recv_lo/recv_hi, ordered after the halo.stream work so far
+ *            → fs3d_slab_step_interior (overlaps with the exchange)
+ *            → fs3d_slab_step_finish (flips buffers, ++step).
+ * At a global boundary the ghost plane is STONE and must not be overwritten. */
+int  fs3d_slab_halo(fs3d_world *w, int back, fs3d_halo *out);
+int  fs3d_slab_step_edges(fs3d_world *w);
+int  fs3d_slab_step_interior(fs3d_world *w);
+int  fs3d_slab_step_finish(fs3d_world *w);
+
+const char *fs3d_last_error(void);
+int  fs3d_schedule_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FS3D_H */

@@ -1,0 +1,37 @@
+"""Generates tests/golden/digests.json from the C oracle (run from the repo root).
+
+There is no reference implementation to generate vectors from; these vectors pin
+the oracle against regressions and give the -m gpu tests committed targets."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import oracle  # noqa: E402
+
+CASES = [
+    # name, dims, scene, scene_seed, seed, checkpoints
+    ("config1_64_sand_block", (64, 64, 64), 1, 1, 1, [1, 2, 3, 4, 10, 50, 100, 250, 500]),
+    ("mixed_64", (64, 64, 64), 2, 1, 1, [1, 2, 3, 4, 8, 64, 200]),
+    ("random_96x40x24", (96, 40, 24), 3, 1, 7, [1, 2, 3, 4, 5, 6, 7, 8, 40]),
+    ("mixed_noise_128x48x32", (128, 48, 32), 4, 3, 9, [1, 4, 16, 60]),
+    ("odd_dims_32x7x5", (32, 7, 5), 3, 2, 3, [1, 2, 3, 4, 9]),
+]
+
+out = {"schedule_version": oracle.lib().fs3d_oracle_schedule_version(), "cases": []}
+for name, dims, scene, sseed, seed, cps in CASES:
+    nx, ny, nz = dims
+    g = oracle.generate(nx, ny, nz, scene, sseed)
+    case = {"name": name, "dims": list(dims), "scene": scene, "scene_seed": sseed, "seed": seed,
+            "digest0": hex(oracle.digest(g)), "digests": []}
+    t = 0
+    for upto in cps:
+        oracle.run(g, seed, t, upto - t)
+        t = upto
+        case["digests"].append([upto, hex(oracle.digest(g))])
+    case["histogram"] = [int(v) for v in oracle.histogram(g)[:4]]
+    out["cases"].append(case)
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "digests.json"), "w") as f:
+    json.dump(out, f, indent=1)
+print("wrote digests.json")

@@ -1,0 +1,72 @@
+"""CPU tests of the drop-in boundary: libfs3d.so builds, loads, exports every symbol include/fs3d.h
+declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fs3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fs3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(fs3d):
+    from fallingsand3d_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_library_exports_every_declared_symbol(fs3d):
+    from fallingsand3d_b200 import _lib
+    lib = C.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+    assert lib.fs3d_schedule_version() == 1
+
+
+def test_sass_is_sm100a_with_256bit_accesses(fs3d):
+    import shutil
+    import subprocess
+    from fallingsand3d_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "LDG.E" in out and ".256" in out, "step kernel should use 256-bit global loads"
+    assert "STG.E" in out
+
+
+def _has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_cuda(), reason="only meaningful on a box without a GPU")
+def test_no_gpu_means_loud_failure_not_fallback(fs3d):
+    with pytest.raises(fs3d.Fs3dError) as ei:
+        fs3d.VoxelWorld(32, 8, 8)
+    assert ei.value.code in (-5, -6)
+    assert "ERROR" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    # the oracle is test infrastructure: nothing under fallingsand3d_b200/ may import, include,
+    # link or dlopen it (comments citing it are fine)
+    pkg = os.path.join(ROOT, "fallingsand3d_b200")
+    bad = re.compile(r"^\s*(import\s+oracle|from\s+oracle|from\s+\.\.?oracle)|#\s*include\s*[\"<][^\">]*oracle|"
+                     r"libfs3d_oracle|oracle\.(step|run|lib)\(", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not bad.search(text), os.path.join(dirpath, f)

@@ -1,0 +1,151 @@
+"""GPU parity tests: the CUDA step (through the C ABI) against the CPU oracle, bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+E, S, W, X = 0, 1, 2, 3
+
+
+def run_and_compare(fs3d, oracle, nx, ny, nz, scene, seed, steps, every=1, scene_seed=5):
+    g = oracle.generate(nx, ny, nz, scene, scene_seed)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=seed) as w:
+        w.upload(g)
+        assert w.digest() == oracle.digest(g)
+        t = 0
+        while t < steps:
+            n = min(every, steps - t)
+            w.step(n)
+            oracle.run(g, seed, t, n)
+            t += n
+            got = w.download()
+            if not np.array_equal(got, g):
+                bad = np.argwhere(got != g)
+                raise AssertionError(f"{nx}x{ny}x{nz} scene {scene}: mismatch after step {t}: {len(bad)} cells, "
+                                     f"first (z,y,x)={bad[0].tolist()} got {got[tuple(bad[0])]} want {g[tuple(bad[0])]}")
+        assert w.step_index == steps
+        assert w.digest() == oracle.digest(g)
+        assert np.array_equal(w.histogram(), oracle.histogram(g))
+
+
+# every kernel instantiation: J=1 with row groups (nx < 1024), J=1 full warp, J=2, J=4;
+# odd/even ny and nz; ny, nz = 1
+@pytest.mark.parametrize("dims", [(32, 8, 6), (64, 9, 5), (96, 7, 3), (128, 16, 4), (32, 1, 1), (32, 2, 1), (32, 1, 2),
+                                  (256, 12, 9), (1024, 6, 5), (1056, 5, 4), (2048, 6, 4), (2080, 4, 3), (4096, 4, 3)])
+def test_small_grids_every_step(fs3d, oracle, dims):
+    nx, ny, nz = dims
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=3, seed=7, steps=12, every=1)
+
+
+def test_many_warps_and_segments(fs3d, oracle):
+    # enough rows that warps split marches into segments with lead-ins
+    run_and_compare(fs3d, oracle, 64, 200, 40, scene=3, seed=3, steps=8, every=2)
+    run_and_compare(fs3d, oracle, 2048, 64, 10, scene=4, seed=4, steps=8, every=4)
+
+
+def test_config1_64cubed_sand_block_500_steps(fs3d, oracle):
+    # BASELINE config 1, digest compared every step
+    nx = ny = nz = 64
+    g = oracle.generate(nx, ny, nz, 1, 1)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=1) as w:
+        w.generate(fs3d.SCENE_SAND_BLOCK, 1)
+        assert np.array_equal(w.download(), g)
+        for t in range(500):
+            w.step(1)
+            oracle.step(g, 1, t)
+            assert w.digest() == oracle.digest(g), f"step {t + 1}"
+        h = w.histogram()
+        assert h[E] == 258048 and h[S] == 4096
+        assert np.array_equal(w.download(), g)
+
+
+def test_config2_256cubed_mixed_1000_steps(fs3d, oracle):
+    # BASELINE config 2: digest every 10 steps, full compare at the end, histogram invariant
+    n = 256
+    g = oracle.generate(n, n, n, 2, 1)
+    with fs3d.VoxelWorld(n, n, n, seed=1) as w:
+        w.generate(fs3d.SCENE_MIXED, 1)
+        assert w.digest() == oracle.digest(g)
+        h0 = w.histogram()
+        for t in range(0, 1000, 10):
+            w.step(10)
+            oracle.run(g, 1, t, 10)
+            assert w.digest() == oracle.digest(g), f"step {t + 10}"
+        assert np.array_equal(w.histogram(), h0)
+        assert np.array_equal(w.download(), g)
+
+
+def test_golden_digests_on_gpu(fs3d):
+    with open(os.path.join(GOLDEN, "digests.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        nx, ny, nz = case["dims"]
+        with fs3d.VoxelWorld(nx, ny, nz, seed=case["seed"]) as w:
+            w.generate(case["scene"], case["scene_seed"])
+            assert w.digest() == int(case["digest0"], 16), case["name"]
+            t = 0
+            for upto, dg in case["digests"]:
+                w.step(upto - t)
+                t = upto
+                assert w.digest() == int(dg, 16), f"{case['name']} step {upto}"
+            assert [int(v) for v in w.histogram()[:4]] == case["histogram"]
+
+
+@pytest.mark.parametrize("scene", [1, 2, 3, 4])
+def test_device_scene_generators_match_oracle(fs3d, oracle, scene):
+    for dims in [(64, 64, 64), (96, 40, 24), (128, 33, 17)]:
+        nx, ny, nz = dims
+        with fs3d.VoxelWorld(nx, ny, nz) as w:
+            w.generate(scene, 11)
+            assert np.array_equal(w.download(), oracle.generate(nx, ny, nz, scene, 11))
+
+
+def test_cell_access_and_errors(fs3d):
+    with fs3d.VoxelWorld(64, 16, 8, seed=2) as w:
+        assert w.get_cell(3, 4, 5) == E
+        w.set_cell(3, 4, 5, S)
+        assert w.get_cell(3, 4, 5) == S
+        w.fill_box((0, 0, 0), (64, 1, 8), X)
+        h = w.histogram()
+        assert h[X] == 64 * 8 and h[S] == 1
+        with pytest.raises(fs3d.Fs3dError) as ei:
+            w.set_cell(64, 0, 0, S)
+        assert ei.value.code == -4
+        with pytest.raises(fs3d.Fs3dError) as ei:
+            w.set_cell(0, 0, 0, 4)
+        assert ei.value.code == -3
+        bad = np.zeros(w.shape, np.uint8)
+        bad[1, 2, 3] = 9
+        before = w.download()
+        with pytest.raises(fs3d.Fs3dError) as ei:
+            w.upload(bad)
+        assert ei.value.code == -3
+        assert np.array_equal(w.download(), before)   # a rejected upload leaves the world untouched
+        v = w.volume_view(0)
+        assert v["nx"] == 64 and v["z0"] == 0 and v["z1"] == 8 and v["pitch_z"] == 64 * 16 and v["dev_ptr"]
+    with pytest.raises(fs3d.Fs3dError) as ei:
+        fs3d.VoxelWorld(48, 8, 8)
+    assert ei.value.code == -2
+
+
+def test_full_size_properties_1024(fs3d):
+    # size-independent properties at a BASELINE size the oracle cannot follow step by step:
+    # exact conservation, determinism (same seed -> same digest), seed sensitivity
+    n = 1024
+    digs = []
+    for seed in (1, 1, 2):
+        with fs3d.VoxelWorld(n, n, n, seed=seed) as w:
+            w.generate(fs3d.SCENE_RANDOM, 1)
+            h0 = w.histogram()
+            w.step(24)
+            assert np.array_equal(w.histogram(), h0)
+            digs.append(w.digest())
+    assert digs[0] == digs[1] and digs[0] != digs[2]
+
+
+def test_subvolume_of_large_grid_matches_oracle(fs3d, oracle):
+    # 2048-wide rows (J = 2 kernel) at full x extent, short in y/z so the oracle finishes in seconds
+    run_and_compare(fs3d, oracle, 2048, 96, 24, scene=3, seed=5, steps=16, every=8)
