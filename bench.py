@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -68,17 +68,27 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def wait_ready(self, timeout=5.0):
+        """nvidia-smi takes a while to start: block until its first sample has arrived."""
+        t0 = time.time()
+        while self.proc and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Call right before the timed region: only later samples are reported."""
+        self.first = len(self.samples)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
-        for s in self.samples:
+        for s in self.samples[getattr(self, "first", 0):]:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 9:
                 continue
@@ -118,27 +128,37 @@ def cpu_oracle_rate(nx, ny, nz_sample, steps, seed=1):
 
 
 def reference_arm(args):
-    """--impl reference: the CPU oracle (kind "port") on all host threads, bounded sample."""
+    """--impl reference: the CPU oracle (kind "port") on all host threads, bounded sample.
+
+    Each step is one oracle step of a fixed slab sample of the workload (~64 Mi voxels), so the whole
+    --steps K --warmup W run ends within a few minutes whatever K is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import oracle
     n = args.size
-    nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))        # ~64 Mi voxels per step
-    rates = []
+    nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))
+    zlo = n // 2 - nz_sample // 2
+    g = oracle.generate(n, n, n, SCENE_MIXED_NOISE, 1, zlo, zlo + nz_sample)
+    sample = f"{n}x{n}x{nz_sample} slab (z from {zlo}) of the {n}^3 MIXED_NOISE scene, one oracle step per bench step"
+    t = 0
     for _ in range(args.warmup):
-        cpu_oracle_rate(n, n, nz_sample, 1)
+        oracle.step(g, 1, t); t += 1
     t0 = time.perf_counter()
-    total_ms = 0.0
-    cores = 1
-    sample = ""
     for _ in range(args.steps):
-        r, cores, dt, sample = cpu_oracle_rate(n, n, nz_sample, 1)
-        rates.append(r)
-        total_ms += dt * 1e3
-    value = sum(rates) / len(rates)
+        oracle.step(g, 1, t); t += 1
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    if os.environ.get("OMP_NUM_THREADS"):
+        cores = min(cores, int(os.environ["OMP_NUM_THREADS"]))
+    value = n * n * nz_sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{n}^3 MIXED_NOISE scene (BASELINE configs[3]); CPU oracle on a bounded sample",
                    "grid": [n, n, n], "sample": sample},
@@ -180,10 +200,12 @@ def ours(args):
         w = fs3d.VoxelWorld(n, n, n, seed=1)
         w.generate(SCENE_MIXED_NOISE, 1)
         h0 = w.histogram()
-        w.step(Wm)
-        w.sync()
         sampler = ClockSampler(local_rank)
         sampler.start()
+        sampler.wait_ready()
+        w.step(Wm)
+        w.sync()
+        sampler.mark()
         ms, launches = w.step_timed(K)
         clocks = sampler.stop()
         assert np.array_equal(w.histogram(), h0), "material counts changed: invalid run"
@@ -192,13 +214,15 @@ def ours(args):
         sw = SlabWorld(n, n, n, seed=1)
         sw.generate(SCENE_MIXED_NOISE, 1)
         h0 = sw.histogram()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            sampler.wait_ready()
         sw.step(Wm)
         sw.sync()
         dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.mark()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st = sw.engine.stream
         ev0.record(st)
@@ -221,7 +245,12 @@ def ours(args):
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region (N = 1 path) ----
     e2e = None
-    if world_size == 1:
+    if args.e2e_steps <= 0:
+        if world_size == 1:
+            w.close()
+        else:
+            sw.close()
+    elif world_size == 1:
         host = torch.empty((n, n, n), dtype=torch.uint8, pin_memory=True)
         hv = host.numpy()
         w.download(hv)
@@ -271,7 +300,7 @@ def ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None
     if world_size == 1 and not args.no_cpu:
-        nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))
+        nz_sample = max(2, min(n, (1 << 28) // (n * n) or 2))     # ~256 Mi voxels per step: 10-30 s in all
         rate, cores, dt, sample = cpu_oracle_rate(n, n, nz_sample, args.cpu_steps)
         cpu = {"value": rate, "unit": "voxel-updates/s", "cores": cores, "kind": "port", "sample": sample,
                "seconds": dt, "note": "builder-written CPU oracle of the same schedule (the reference has no CPU "
@@ -309,12 +338,12 @@ def ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

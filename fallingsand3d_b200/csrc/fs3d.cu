@@ -413,8 +413,9 @@ int fs3d_create(const fs3d_desc *desc, fs3d_world **out) {
     uint32_t zb = 0;
     for (int i = 0; i < n; ++i) {
         uint64_t ze = (uint64_t)desc->nz * (i + 1) / n;
-        if (i + 1 < n && (ze & 1) && ze + 1 < desc->nz) ze += 1;
-        if (ze <= zb) ze = zb + 1;
+        if (i + 1 < n && (ze & 1)) ze += 1;                                  // prefer even boundaries
+        ze = std::min<uint64_t>(ze, (uint64_t)desc->nz - (uint64_t)(n - 1 - i)); // leave a plane for every later slab
+        ze = std::max<uint64_t>(ze, (uint64_t)zb + 1);
         if (i + 1 == n) ze = desc->nz;
         w->slabs[i].device = w->devices[i];
         w->slabs[i].z0 = zb;

@@ -20,20 +20,20 @@ import torch.distributed as dist
 
 def slab_bounds(nz, world_size):
     """Contiguous z-ranges, boundaries on even planes where possible (the same rule as fs3d_create)."""
+    if world_size > nz:
+        raise ValueError("more ranks than z-planes")
     bounds = []
     zb = 0
     for i in range(world_size):
         ze = nz * (i + 1) // world_size
-        if i + 1 < world_size and (ze & 1) and ze + 1 < nz:
-            ze += 1
-        if ze <= zb:
-            ze = zb + 1
+        if i + 1 < world_size and (ze & 1):
+            ze += 1                                   # prefer even boundaries
+        ze = min(ze, nz - (world_size - 1 - i))       # leave a plane for every later rank
+        ze = max(ze, zb + 1)
         if i + 1 == world_size:
             ze = nz
         bounds.append((zb, ze))
         zb = ze
-    if bounds[-1][0] >= bounds[-1][1]:
-        raise ValueError("more ranks than z-planes")
     return bounds
 
 

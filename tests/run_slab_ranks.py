@@ -1,0 +1,57 @@
+"""Launched under torchrun on >= 2 GPUs (see test_slab_nccl_gpu.py): SlabWorld over NCCL must
+reproduce the single-GPU world's digest step by step, and the oracle's on a small grid."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import fallingsand3d_b200 as fs3d  # noqa: E402
+from fallingsand3d_b200.slab import SlabWorld  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for (nx, ny, nz, scene, steps) in [(64, 24, 18, 3, 12), (2048, 32, 24, 4, 10), (256, 256, 256, 2, 40)]:
+        sw = SlabWorld(nx, ny, nz, seed=5)
+        sw.generate(scene, 3)
+        ref = None
+        if rank == 0:
+            ref = fs3d.VoxelWorld(nx, ny, nz, seed=5)
+            ref.generate(scene, 3)
+        for t in range(steps):
+            sw.step(1)
+            d = sw.digest()
+            if rank == 0:
+                ref.step(1)
+                if ref.digest() != d:
+                    ok = False
+                    print(f"MISMATCH {nx}x{ny}x{nz} step {t + 1}", flush=True)
+                    break
+        h = sw.histogram()
+        if rank == 0:
+            ok = ok and np.array_equal(h, ref.histogram())
+            ref.close()
+        sw.close()
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        ok = bool(flag.item())
+        if not ok:
+            break
+    if rank == 0:
+        print("SLAB_NCCL_OK" if ok else "SLAB_NCCL_FAIL", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""CPU tests (gloo, world_size 2 and 3) of the N>1 host logic in fallingsand3d_b200/slab.py:
+z-slab partition, one-plane halo exchange per step, global digest/histogram reductions.  The
+compute engine is the CPU oracle here; the same SlabWorld drives libfs3d on the GPUs."""
+import numpy as np
+import pytest
+
+from fallingsand3d_b200.slab import slab_bounds
+from tests.slab_helpers import OracleSlabEngine, run_ranks
+
+
+def test_slab_bounds_cover_and_prefer_even_boundaries():
+    for nz in (2, 3, 7, 10, 64, 255, 2048):
+        for ws in (1, 2, 3, 4, 8):
+            if ws > nz:
+                continue
+            b = slab_bounds(nz, ws)
+            assert b[0][0] == 0 and b[-1][1] == nz
+            assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+            assert all(lo < hi for lo, hi in b)
+    assert slab_bounds(2048, 8) == [(256 * i, 256 * (i + 1)) for i in range(8)]
+    assert all(lo % 2 == 0 for lo, _ in slab_bounds(250, 4))
+
+
+def _worker(rank, world_size, dims, scene, seed, steps):
+    from fallingsand3d_b200.slab import SlabWorld
+    nx, ny, nz = dims
+    sw = SlabWorld(nx, ny, nz, seed=seed, engine_factory=OracleSlabEngine)
+    sw.generate(scene, 4)
+    h0 = sw.histogram()
+    digests = [sw.digest()]
+    for _ in range(steps):
+        sw.step(1)
+        digests.append(sw.digest())
+    assert np.array_equal(sw.histogram(), h0)
+    whole = sw.gather()
+    return digests, whole, [int(v) for v in h0[:4]], sw.exchanges, (sw.z_begin, sw.z_end)
+
+
+@pytest.mark.parametrize("world_size,dims", [(2, (32, 12, 10)), (3, (64, 9, 11)), (2, (32, 8, 3))])
+def test_slab_world_matches_whole_grid_oracle(oracle, world_size, dims):
+    nx, ny, nz = dims
+    steps, seed, scene = 9, 21, 3
+    out = run_ranks(world_size, _worker, dims, scene, seed, steps)
+    g = oracle.generate(nx, ny, nz, scene, 4)
+    want = [oracle.digest(g)]
+    for t in range(steps):
+        oracle.step(g, seed, t)
+        want.append(oracle.digest(g))
+    for rank, (digests, whole, h, exchanges, zr) in enumerate(out):
+        assert digests == want, f"rank {rank}"
+        assert np.array_equal(whole, g)
+        assert h == [int(v) for v in oracle.histogram(oracle.generate(nx, ny, nz, scene, 4))[:4]]
+        assert exchanges == steps + 1          # one per step + the initial refresh
+    assert [o[4] for o in out] == slab_bounds(nz, world_size)
+
+
+def test_u64_allreduce_wraps_like_the_digest():
+    out = run_ranks(2, _wrap_worker)
+    assert out[0] == out[1] == [(2 ** 64 - 5 + 2 ** 63 + 11) % 2 ** 64, 7]
+
+
+def _wrap_worker(rank, world_size):
+    from fallingsand3d_b200.slab import SlabWorld
+    sw = SlabWorld(32, 4, 4, engine_factory=OracleSlabEngine)
+    vals = np.array([2 ** 64 - 5, 3] if rank == 0 else [2 ** 63 + 11, 4], dtype=np.uint64)
+    return [int(v) for v in sw._allreduce_u64(vals)]
