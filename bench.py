@@ -310,7 +310,7 @@ def ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(str(n))
+            traffic = json.load(f).get(str(n)) if world_size == 1 else None
 
     line = {
         "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": world_size, "steps": K, "warmup": Wm,

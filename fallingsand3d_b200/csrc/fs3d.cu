@@ -30,7 +30,8 @@ struct Slab {
     uint8_t *buf[2] = {nullptr, nullptr};   // (nzl + 2) planes each; plane 0 / nzl+1 are ghosts
     size_t bytes = 0;
     cudaStream_t s_main = nullptr, s_comm = nullptr;
-    cudaEvent_t ev_edges = nullptr, ev_done = nullptr, ev_halo_lo = nullptr, ev_halo_hi = nullptr;
+    cudaEvent_t ev_edges = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_out_lo = nullptr, ev_out_hi = nullptr;   // my edge plane has landed in the lower / upper neighbour's ghost
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     unsigned long long *d_scratch = nullptr;   // 256 + 1 u64 + 1 u32 flag
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
@@ -96,7 +97,7 @@ static int init_slab(fs3d_world *w, Slab &s) {
     for (int b = 0; b < 2; ++b) FS3D_CUDA(cudaMalloc(&s.buf[b], s.bytes));
     FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_main, cudaStreamNonBlocking));
     FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
-    cudaEvent_t *evs[] = {&s.ev_edges, &s.ev_done, &s.ev_halo_lo, &s.ev_halo_hi};
+    cudaEvent_t *evs[] = {&s.ev_edges, &s.ev_done, &s.ev_out_lo, &s.ev_out_hi};
     for (auto e : evs) FS3D_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     FS3D_CUDA(cudaEventCreate(&s.ev_t0));
     FS3D_CUDA(cudaEventCreate(&s.ev_t1));
@@ -130,7 +131,7 @@ static void free_slab(Slab &s) {
     if (s.d_skip) cudaFree(s.d_skip);
     if (s.d_last_active) cudaFree(s.d_last_active);
     if (s.d_tiles_run) cudaFree(s.d_tiles_run);
-    cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_halo_lo, s.ev_halo_hi, s.ev_t0, s.ev_t1};
+    cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_out_lo, s.ev_out_hi, s.ev_t0, s.ev_t1};
     for (auto e : evs) if (e) cudaEventDestroy(e);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_comm) cudaStreamDestroy(s.s_comm);
@@ -212,13 +213,13 @@ static int exchange_halos(fs3d_world *w) {
             FS3D_CUDA(cudaStreamWaitEvent(s.s_comm, d.ev_done, 0));   // d finished reading that ghost last step
             FS3D_CUDA(cudaMemcpyPeerAsync(d.buf[back] + pb * ((size_t)d.nzl + 1), d.device,
                                           s.buf[back] + pb, s.device, pb, s.s_comm));
-            FS3D_CUDA(cudaEventRecord(d.ev_halo_hi, s.s_comm));
+            FS3D_CUDA(cudaEventRecord(s.ev_out_lo, s.s_comm));   // events live on the recording stream's device
         }
         if (i + 1 < n) {   // my last owned plane -> upper neighbour's ghost-low
             Slab &d = w->slabs[i + 1];
             FS3D_CUDA(cudaStreamWaitEvent(s.s_comm, d.ev_done, 0));
             FS3D_CUDA(cudaMemcpyPeerAsync(d.buf[back], d.device, s.buf[back] + pb * (size_t)s.nzl, s.device, pb, s.s_comm));
-            FS3D_CUDA(cudaEventRecord(d.ev_halo_lo, s.s_comm));
+            FS3D_CUDA(cudaEventRecord(s.ev_out_hi, s.s_comm));
         }
     }
     return FS3D_OK;
@@ -239,8 +240,9 @@ static int step_once(fs3d_world *w) {
             FS3D_CUDA(cudaSetDevice(s.device));
             // ghosts of the front buffer must have arrived (written during the previous step)
             if (w->halo_pending) {
-                FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_halo_lo, 0));
-                FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_halo_hi, 0));
+                const int i = (int)(&s - &w->slabs[0]);
+                if (i > 0) FS3D_CUDA(cudaStreamWaitEvent(s.s_main, w->slabs[i - 1].ev_out_hi, 0));
+                if (i + 1 < n) FS3D_CUDA(cudaStreamWaitEvent(s.s_main, w->slabs[i + 1].ev_out_lo, 0));
             }
             PairLayout L = pair_layout(s, hoff);
             int rc = launch_pairs(w, s, 0, 1);
