@@ -37,7 +37,7 @@ struct Slab {
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
     float *d_palette = nullptr;
     int num_sms = 0;
-    int blocks_per_sm[3][2][2] = {};   // [Jidx][OX][TODD]
+    int blocks_per_sm[2][2][2] = {};   // [SKIP][OX][TODD] for this world's J
     // settled-tile skipping
     uint8_t *d_skip = nullptr;
     uint32_t *d_last_active = nullptr;
@@ -67,17 +67,17 @@ namespace fs3d {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
 typedef void (*StepFn)(const StepParams);
-static StepFn step_fn(int jidx, int ox, int todd) {
-    static StepFn tab[3][2][2] = {
-        {{step_kernel<1, 0, 0, STEP_THREADS>, step_kernel<1, 0, 1, STEP_THREADS>},
-         {step_kernel<1, 1, 0, STEP_THREADS>, step_kernel<1, 1, 1, STEP_THREADS>}},
-        {{step_kernel<2, 0, 0, STEP_THREADS>, step_kernel<2, 0, 1, STEP_THREADS>},
-         {step_kernel<2, 1, 0, STEP_THREADS>, step_kernel<2, 1, 1, STEP_THREADS>}},
-        {{step_kernel<4, 0, 0, STEP_THREADS>, step_kernel<4, 0, 1, STEP_THREADS>},
-         {step_kernel<4, 1, 0, STEP_THREADS>, step_kernel<4, 1, 1, STEP_THREADS>}},
+#define FS3D_ROW(J, SK) \
+    {{step_kernel<J, 0, 0, SK, STEP_THREADS>, step_kernel<J, 0, 1, SK, STEP_THREADS>}, \
+     {step_kernel<J, 1, 0, SK, STEP_THREADS>, step_kernel<J, 1, 1, SK, STEP_THREADS>}}
+static StepFn step_fn(int jidx, int ox, int todd, int skip) {
+    static StepFn tab[2][3][2][2] = {
+        {FS3D_ROW(1, 0), FS3D_ROW(2, 0), FS3D_ROW(4, 0)},
+        {FS3D_ROW(1, 1), FS3D_ROW(2, 1), FS3D_ROW(4, 1)},
     };
-    return tab[jidx][ox][todd];
+    return tab[skip][jidx][ox][todd];
 }
+constexpr uint32_t YTILE_LOG2 = 5, ZTILE_LOG2 = 3;   // activity tile = nx x 32 x 8 voxels
 
 static size_t plane_bytes(const fs3d_world *w) { return (size_t)w->desc.nx * w->desc.ny; }
 static uint8_t *owned_ptr(const fs3d_world *w, const Slab &s, int b) { return s.buf[b] + plane_bytes(w); }
@@ -104,12 +104,24 @@ static int init_slab(fs3d_world *w, Slab &s) {
     FS3D_CUDA(cudaMalloc(&s.d_scratch, 260 * sizeof(unsigned long long)));
     FS3D_CUDA(cudaMalloc(&s.d_palette, 256 * 4 * sizeof(float)));
     FS3D_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, s.device));
-    for (int ox = 0; ox < 2; ++ox)
-        for (int td = 0; td < 2; ++td) {
-            int nb = 0;
-            FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td), STEP_THREADS, 0));
-            s.blocks_per_sm[w->jidx][ox][td] = std::max(nb, 1);
-        }
+    for (int sk = 0; sk < 2; ++sk)
+        for (int ox = 0; ox < 2; ++ox)
+            for (int td = 0; td < 2; ++td) {
+                int nb = 0;
+                FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk), STEP_THREADS, 0));
+                s.blocks_per_sm[sk][ox][td] = std::max(nb, 1);
+            }
+    if (w->desc.flags & FS3D_FLAG_SKIP_SETTLED) {
+        s.nztiles = (s.nzl + (1u << ZTILE_LOG2) - 1) >> ZTILE_LOG2;
+        s.nytiles = (w->desc.ny + (1u << YTILE_LOG2) - 1) >> YTILE_LOG2;
+        const size_t nt = (size_t)s.nztiles * s.nytiles;
+        FS3D_CUDA(cudaMalloc(&s.d_skip, nt));
+        FS3D_CUDA(cudaMalloc(&s.d_last_active, nt * sizeof(uint32_t)));
+        FS3D_CUDA(cudaMalloc(&s.d_tiles_run, 2 * sizeof(unsigned long long)));
+        FS3D_CUDA(cudaMemsetAsync(s.d_skip, 0, nt, s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_last_active, 0, nt * sizeof(uint32_t), s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, 2 * sizeof(unsigned long long), s.s_main));
+    }
     // both buffers start as EMPTY with STONE ghost planes (closed box / not-yet-exchanged halo)
     for (int b = 0; b < 2; ++b) {
         FS3D_CUDA(cudaMemsetAsync(s.buf[b], 0, s.bytes, s.s_main));
@@ -181,21 +193,51 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe) {
     p.nit = w->desc.ny / 2 + 1;
     p.key_xy = step_key(w->desc.seed, t, 0);
     p.key_zy = step_key(w->desc.seed, t, 1);
-    p.skip = nullptr; p.last_active = nullptr;
+    const int sk = s.d_skip ? 1 : 0;
+    p.skip = s.d_skip; p.last_active = s.d_last_active;
+    p.ytile_log2 = YTILE_LOG2; p.ztile_log2 = ZTILE_LOG2; p.nytiles = s.nytiles;
     p.step_plus1 = (uint32_t)(t + 1);
 
     const uint64_t npg = ((uint64_t)(pe - pb) + w->groups - 1) / w->groups;
     const uint64_t total = npg * p.nit;
     // enough warps to fill the machine, but never fewer than ~8 iterations per warp
-    const int bps = s.blocks_per_sm[w->jidx][hoff][todd];
+    const int bps = s.blocks_per_sm[sk][hoff][todd];
     uint64_t max_blocks = (uint64_t)s.num_sms * bps;
     const uint64_t warps_per_block = STEP_THREADS / 32;
     uint64_t want_warps = std::max<uint64_t>(1, total / 8);
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
-    step_fn(w->jidx, (int)hoff, (int)todd)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
+    step_fn(w->jidx, (int)hoff, (int)todd, sk)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
+    return FS3D_OK;
+}
+
+// settled-tile skipping: recompute the skip map of one slab for the step about to run
+static int launch_skip_map(fs3d_world *w, Slab &s) {
+    if (!s.d_skip) return FS3D_OK;
+    const uint32_t nt = s.nztiles * s.nytiles;
+    FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, sizeof(unsigned long long), s.s_main));
+    const int has_lo = s.z0 > 0, has_hi = s.z0 + s.nzl < w->desc.nz;
+    skip_map_kernel<<<std::max(1u, std::min((nt + 255u) / 256u, 1024u)), 256, 0, s.s_main>>>(
+        s.d_last_active, s.d_skip, s.nztiles, s.nytiles, (uint32_t)w->step, has_lo, has_hi, s.d_tiles_run);
+    FS3D_CUDA(cudaGetLastError());
+    w->launches++;
+    return FS3D_OK;
+}
+
+// after the front buffer was edited from outside the step (upload / generate / set_cell / fill_box):
+// every tile counts as active "just now", so the next four steps run everywhere
+static int touch_all_tiles(fs3d_world *w) {
+    for (auto &s : w->slabs) {
+        if (!s.d_skip) continue;
+        FS3D_CUDA(cudaSetDevice(s.device));
+        const uint64_t nt = (uint64_t)s.nztiles * s.nytiles;
+        // last_active holds (step + 1); "active at step - 1" = step; a fresh world (step 0) holds 0
+        std::vector<uint32_t> v(nt, (uint32_t)w->step);
+        FS3D_CUDA(cudaMemcpyAsync(s.d_last_active, v.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, s.s_main));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    }
     return FS3D_OK;
 }
 
@@ -232,7 +274,8 @@ static int step_once(fs3d_world *w) {
         Slab &s = w->slabs[0];
         FS3D_CUDA(cudaSetDevice(s.device));
         PairLayout L = pair_layout(s, hoff);
-        int rc = launch_pairs(w, s, 0, L.npairs);
+        int rc = launch_skip_map(w, s);
+        if (!rc) rc = launch_pairs(w, s, 0, L.npairs);
         if (rc) return rc;
     } else {
         // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
@@ -245,7 +288,8 @@ static int step_once(fs3d_world *w) {
                 if (i + 1 < n) FS3D_CUDA(cudaStreamWaitEvent(s.s_main, w->slabs[i + 1].ev_out_lo, 0));
             }
             PairLayout L = pair_layout(s, hoff);
-            int rc = launch_pairs(w, s, 0, 1);
+            int rc = launch_skip_map(w, s);
+            if (!rc) rc = launch_pairs(w, s, 0, 1);
             if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs);
             if (rc) return rc;
             FS3D_CUDA(cudaEventRecord(s.ev_edges, s.s_main));
@@ -269,6 +313,7 @@ static int step_once(fs3d_world *w) {
 // in-process slabs (and leave STONE at the global boundary).
 static int refresh_ghosts(fs3d_world *w) {
     const int n = (int)w->slabs.size();
+    { int rc = touch_all_tiles(w); if (rc) return rc; }
     if (n <= 1 || w->external) return FS3D_OK;
     const size_t pb = plane_bytes(w);
     for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); FS3D_CUDA(cudaStreamSynchronize(s.s_main)); FS3D_CUDA(cudaStreamSynchronize(s.s_comm)); }
@@ -534,7 +579,7 @@ int fs3d_set_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t m) 
     uint8_t *p = owned_ptr(w, *s, w->cur) + x + (size_t)w->desc.nx * (y + (size_t)w->desc.ny * (z - s->z0));
     FS3D_CUDA(cudaMemcpy(p, &m, 1, cudaMemcpyHostToDevice));
     if (z == s->z0 || z == s->z0 + s->nzl - 1) return refresh_ghosts(w);
-    return FS3D_OK;
+    return touch_all_tiles(w);
 }
 
 int fs3d_get_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t *m) {
@@ -679,6 +724,16 @@ int fs3d_digest(fs3d_world *w, uint64_t *out) {
 int fs3d_activity(fs3d_world *w, uint64_t *tiles_run, uint64_t *tiles_total) {
     if (!w || !tiles_run || !tiles_total) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
     *tiles_run = 0; *tiles_total = 0;
+    int rc = sync_all(w);
+    if (rc) return rc;
+    for (auto &s : w->slabs) {
+        if (!s.d_skip) { *tiles_run += 1; *tiles_total += 1; continue; }   // skipping off: everything runs
+        FS3D_CUDA(cudaSetDevice(s.device));
+        unsigned long long st[2] = {0, 0};
+        FS3D_CUDA(cudaMemcpy(st, s.d_tiles_run, sizeof(st), cudaMemcpyDeviceToHost));
+        *tiles_run += st[0];
+        *tiles_total += st[1] ? st[1] : (unsigned long long)s.nztiles * s.nytiles;
+    }
     return FS3D_OK;
 }
 
@@ -752,7 +807,8 @@ int fs3d_slab_step_edges(fs3d_world *w) {
     Slab &s = w->slabs[0];
     FS3D_CUDA(cudaSetDevice(s.device));
     PairLayout L = pair_layout(s, (uint32_t)((w->step >> 1) & 1));
-    int rc = launch_pairs(w, s, 0, 1);
+    int rc = launch_skip_map(w, s);
+    if (!rc) rc = launch_pairs(w, s, 0, 1);
     if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs);
     if (rc) return rc;
     w->edges_phase = 1;

@@ -38,11 +38,11 @@ struct StepParams {
     uint32_t pair_begin, pair_end;   // pairs [begin, end) handled by this launch
     uint32_t nit;            // march iterations per pair: ny / 2 + 1
     uint32_t key_xy, key_zy; // SCHEDULE.md §3 key(seed, t, axis)
-    // settled-tile skipping (nullptr = off)
+    // settled-tile skipping (SKIP = 1 instantiations only)
     const uint8_t *skip;     // [ztiles][ytiles] 1 = tile provably static this step
-    uint32_t *last_active;   // [ztiles][ytiles] step+1 of last enabled block
-    uint32_t ytile_log2;     // y-tile height = 1 << ytile_log2 (even, >= 4)
-    uint32_t ztile_log2;     // z-tile depth (local planes, owned index) = 1 << ztile_log2
+    uint32_t *last_active;   // [ztiles][ytiles] (step + 1) of the last enabled block seen in the tile
+    uint32_t ytile_log2;     // y-tile height = 1 << ytile_log2 planes (>= 2)
+    uint32_t ztile_log2;     // z-tile depth = 1 << ztile_log2 owned planes
     uint32_t nytiles;
     uint32_t step_plus1;     // (uint32)(t + 1)
 };
@@ -62,7 +62,7 @@ template <int J>
 struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u32]
 
 // ---------------------------------------------------------------------------------------------
-template <int J, int OX, int TODD, int THREADS>
+template <int J, int OX, int TODD, int SKIP, int THREADS>
 __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -184,32 +184,81 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
             return en;
         };
 
-        // lead-in: sub-step 1 of the pair below the segment gives `prev` (plane 2·it_a − 1)
-        if (it_a > 0) {
-            load_pair(it_a - 1);
-#pragma unroll
-            for (int j = 0; j < J; ++j)
-#pragma unroll
-                for (int r = 0; r < 2; ++r) { lo[j][r] = pack(raw.w[j][r][0]); hi[j][r] = pack(raw.w[j][r][1]); }
-            const uint32_t y1 = 2u * (it_a - 1);
-            if (TODD == 0) do_xy(hi, lo, y1 + 1); else do_zy(hi, lo, y1 + 1);
-#pragma unroll
-            for (int j = 0; j < J; ++j) { prev[j][0] = hi[j][0]; prev[j][1] = hi[j][1]; }
-        }
+        // settled-tile bookkeeping (SCHEDULE.md §4): y is cut into blocks of BLK iterations; block b
+        // stores planes 2·BLK·b − 1 … 2·BLK·(b+1) − 2, i.e. y-tile b plus the top plane of tile b − 1
+        const uint32_t blk_log2 = SKIP ? p.ytile_log2 - 1u : 31u;
+        const int32_t ozl = (int32_t)lzl - 1, ozr = (int32_t)lzl;      // owned-plane indices of the two rows
+        auto tile_quiet = [&](int32_t oz, uint32_t yt) -> bool {
+            if (oz < 0 || oz >= (int32_t)p.nzl || yt >= p.nytiles) return true;
+            return p.skip[(size_t)((uint32_t)oz >> p.ztile_log2) * p.nytiles + yt] != 0;
+        };
+        auto block_skippable = [&](uint32_t bi) -> bool {
+            bool q = true;
+            if (pair_ok) {
+                q = tile_quiet(ozl, bi) && tile_quiet(ozr, bi);
+                if (bi > 0) q = q && tile_quiet(ozl, bi - 1) && tile_quiet(ozr, bi - 1);
+            }
+            return __all_sync(ONES, q);
+        };
+        auto mark = [&](int32_t oz, uint32_t yt) {
+            if (oz >= 0 && oz < (int32_t)p.nzl && yt < p.nytiles)
+                p.last_active[(size_t)((uint32_t)oz >> p.ztile_log2) * p.nytiles + yt] = p.step_plus1;
+        };
+        uint32_t en_main = 0, en_strad = 0;
+        auto flush_marks = [&](uint32_t bi) {
+            if (en_main | en_strad) { mark(ozl, bi); mark(ozr, bi); }
+            if (en_strad && bi > 0) { mark(ozl, bi - 1); mark(ozr, bi - 1); }
+            en_main = 0; en_strad = 0;
+        };
 
-        load_pair(it_a);
-        for (uint32_t it = it_a; it < it_b; ++it) {
+        bool have_prev = (it_a == 0);      // prev = STONE below the floor
+        bool loaded = false;
+        bool next_skip = SKIP ? block_skippable(it_a >> blk_log2) : false;
+        uint32_t it = it_a;
+        while (it < it_b) {
+            if (SKIP && next_skip) {       // jump over a provably static block; nothing is read or written
+                const uint32_t nb = ((it >> blk_log2) + 1u) << blk_log2;
+                it = nb < it_b ? nb : it_b;
+                have_prev = false; loaded = false;
+                if (it < it_b) next_skip = block_skippable(it >> blk_log2);
+                continue;
+            }
+            if (!have_prev) {
+                // lead-in: sub-step 1 of the pair below gives `prev` (plane 2·it − 1, post sub-step 1)
+                load_pair(it - 1);
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) { lo[j][r] = pack(raw.w[j][r][0]); hi[j][r] = pack(raw.w[j][r][1]); }
+                const uint32_t yl = 2u * (it - 1);
+                if (TODD == 0) do_xy(hi, lo, yl + 1); else do_zy(hi, lo, yl + 1);
+#pragma unroll
+                for (int j = 0; j < J; ++j) { prev[j][0] = hi[j][0]; prev[j][1] = hi[j][1]; }
+                have_prev = true;
+                loaded = false;
+            }
+            if (!loaded) load_pair(it);
+
             const uint32_t y1 = 2u * it;
 #pragma unroll
             for (int j = 0; j < J; ++j)
 #pragma unroll
                 for (int r = 0; r < 2; ++r) { lo[j][r] = pack(raw.w[j][r][0]); hi[j][r] = pack(raw.w[j][r][1]); }
-            if (it + 1 < it_b) load_pair(it + 1);          // in flight while we evaluate this pair
 
-            uint32_t en;
-            if (TODD == 0) { en = do_xy(hi, lo, y1 + 1); en |= do_zy(lo, prev, y1); }
-            else           { en = do_zy(hi, lo, y1 + 1); en |= do_xy(lo, prev, y1); }
-            (void)en;
+            // decide about the next iteration now, so that its loads are in flight while we evaluate
+            const uint32_t nxt = it + 1;
+            const bool boundary = SKIP && (nxt & ((1u << blk_log2) - 1u)) == 0u;
+            if (boundary && nxt < it_b) next_skip = block_skippable(nxt >> blk_log2);
+            loaded = nxt < it_b && !(boundary && next_skip);
+            if (loaded) load_pair(nxt);
+
+            uint32_t e1, e2;
+            if (TODD == 0) { e1 = do_xy(hi, lo, y1 + 1); e2 = do_zy(lo, prev, y1); }
+            else           { e1 = do_zy(hi, lo, y1 + 1); e2 = do_xy(lo, prev, y1); }
+            if (SKIP) {
+                en_main |= e1;
+                if ((it & ((1u << blk_log2) - 1u)) == 0u) en_strad |= e2; else en_main |= e2;
+            }
 
             // planes y1 − 1 (prev) and y1 (lo) are final
 #pragma unroll
@@ -224,8 +273,41 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                 }
 #pragma unroll
             for (int j = 0; j < J; ++j) { prev[j][0] = hi[j][0]; prev[j][1] = hi[j][1]; }
+
+            if (SKIP && (boundary || nxt >= it_b)) flush_marks(it >> blk_log2);
+            it = nxt;
         }
     }
+}
+
+// skip[t] = 1 iff tile t and its 8 neighbours in (z-tile, y-tile) space saw no enabled block during the
+// last four steps (all four offset phases), so nothing in or around it can change at step `t_now`.
+// Edge z-tiles next to another slab are never skipped (the neighbour's activity is not visible here).
+__global__ void skip_map_kernel(const uint32_t *last_active, uint8_t *skip, uint32_t nztiles, uint32_t nytiles,
+                                uint32_t t_now, int has_lo_neighbour, int has_hi_neighbour,
+                                unsigned long long *stats /* [0] tiles run, [1] tiles total (overwritten) */) {
+    const uint32_t n = nztiles * nytiles;
+    uint32_t run = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int zt = (int)(i / nytiles), yt = (int)(i % nytiles);
+        uint32_t newest = 0;   // largest (last active step + 1) in the 3x3 neighbourhood, relative age below
+        bool quiet = true;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy) {
+                int z = zt + dz, y = yt + dy;
+                if (z < 0 || z >= (int)nztiles || y < 0 || y >= (int)nytiles) continue;
+                uint32_t la = last_active[(size_t)z * nytiles + y];
+                // quiet for steps t_now-4 .. t_now-1  <=>  la (= last active step + 1) + 4 <= t_now
+                if ((uint64_t)la + 4ull > (uint64_t)t_now) quiet = false;
+                newest = la > newest ? la : newest;
+            }
+        if ((zt == 0 && has_lo_neighbour) || (zt == (int)nztiles - 1 && has_hi_neighbour)) quiet = false;
+        skip[i] = quiet ? 1 : 0;
+        run += quiet ? 0u : 1u;
+    }
+    for (int o = 16; o > 0; o >>= 1) run += __shfl_xor_sync(0xFFFFFFFFu, run, o);
+    if ((threadIdx.x & 31) == 0 && run) atomicAdd(&stats[0], (unsigned long long)run);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] = n;
 }
 
 }  // namespace fs3d
