@@ -57,6 +57,7 @@ SIGNATURES = {
     "fs3d_raymarch": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "fs3d_raymarch_depth": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fs3d_slab_halo": (C.c_int, [_W, C.c_int, C.POINTER(Halo)]),
+    "fs3d_slab_pass_steps": (C.c_int, [_W, C.c_uint32]),
     "fs3d_slab_step_edges": (C.c_int, [_W]),
     "fs3d_slab_step_interior": (C.c_int, [_W]),
     "fs3d_slab_step_finish": (C.c_int, [_W]),

@@ -37,7 +37,7 @@ struct Slab {
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
     float *d_palette = nullptr;
     int num_sms = 0;
-    int blocks_per_sm[2][2][2] = {};   // [SKIP][OX][TODD] for this world's J
+    int blocks_per_sm[2][2][2][2] = {};   // [NS-1][SKIP][OX][TODD] for this world's J
     // settled-tile skipping
     uint8_t *d_skip = nullptr;
     uint32_t *d_last_active = nullptr;
@@ -61,6 +61,7 @@ struct fs3d_world {
     bool palette_dirty = true;
     float palette[256 * 4];
     int edges_phase = 0;         // external stepping protocol state
+    int pass_ns = 1;             // steps fused in the current external pass
 };
 
 namespace fs3d {
@@ -68,14 +69,20 @@ namespace fs3d {
 // ---- kernel dispatch ----------------------------------------------------------------------------
 typedef void (*StepFn)(const StepParams);
 #define FS3D_ROW(J, SK) \
-    {{step_kernel<J, 0, 0, SK, STEP_THREADS>, step_kernel<J, 0, 1, SK, STEP_THREADS>}, \
-     {step_kernel<J, 1, 0, SK, STEP_THREADS>, step_kernel<J, 1, 1, SK, STEP_THREADS>}}
-static StepFn step_fn(int jidx, int ox, int todd, int skip) {
-    static StepFn tab[2][3][2][2] = {
+    {{step_kernel<J, 0, 0, SK, 1, STEP_THREADS>, step_kernel<J, 0, 1, SK, 1, STEP_THREADS>}, \
+     {step_kernel<J, 1, 0, SK, 1, STEP_THREADS>, step_kernel<J, 1, 1, SK, 1, STEP_THREADS>}}
+#define FS3D_ROW2(J, SK) {step_kernel<J, 0, 0, SK, 2, STEP_THREADS>, step_kernel<J, 1, 0, SK, 2, STEP_THREADS>}
+// ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even
+static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns) {
+    static StepFn tab1[2][3][2][2] = {
         {FS3D_ROW(1, 0), FS3D_ROW(2, 0), FS3D_ROW(4, 0)},
         {FS3D_ROW(1, 1), FS3D_ROW(2, 1), FS3D_ROW(4, 1)},
     };
-    return tab[skip][jidx][ox][todd];
+    static StepFn tab2[2][3][2] = {
+        {FS3D_ROW2(1, 0), FS3D_ROW2(2, 0), FS3D_ROW2(4, 0)},
+        {FS3D_ROW2(1, 1), FS3D_ROW2(2, 1), FS3D_ROW2(4, 1)},
+    };
+    return ns == 2 ? tab2[skip][jidx][ox] : tab1[skip][jidx][ox][todd];
 }
 constexpr uint32_t YTILE_LOG2 = 5, ZTILE_LOG2 = 3;   // activity tile = nx x 32 x 8 voxels
 
@@ -104,13 +111,14 @@ static int init_slab(fs3d_world *w, Slab &s) {
     FS3D_CUDA(cudaMalloc(&s.d_scratch, 260 * sizeof(unsigned long long)));
     FS3D_CUDA(cudaMalloc(&s.d_palette, 256 * 4 * sizeof(float)));
     FS3D_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, s.device));
-    for (int sk = 0; sk < 2; ++sk)
-        for (int ox = 0; ox < 2; ++ox)
-            for (int td = 0; td < 2; ++td) {
-                int nb = 0;
-                FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk), STEP_THREADS, 0));
-                s.blocks_per_sm[sk][ox][td] = std::max(nb, 1);
-            }
+    for (int ns = 1; ns <= 2; ++ns)
+        for (int sk = 0; sk < 2; ++sk)
+            for (int ox = 0; ox < 2; ++ox)
+                for (int td = 0; td < (ns == 2 ? 1 : 2); ++td) {
+                    int nb = 0;
+                    FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns), STEP_THREADS, 0));
+                    s.blocks_per_sm[ns - 1][sk][ox][td] = std::max(nb, 1);
+                }
     if (w->desc.flags & FS3D_FLAG_SKIP_SETTLED) {
         s.nztiles = (s.nzl + (1u << ZTILE_LOG2) - 1) >> ZTILE_LOG2;
         s.nytiles = (w->desc.ny + (1u << YTILE_LOG2) - 1) >> YTILE_LOG2;
@@ -177,7 +185,7 @@ static PairLayout pair_layout(const Slab &s, uint32_t oz) {
     return L;
 }
 
-static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe) {
+static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns) {
     if (pe <= pb) return FS3D_OK;
     const uint64_t t = w->step;
     const uint32_t hoff = (uint32_t)((t >> 1) & 1), todd = (uint32_t)(t & 1);
@@ -190,24 +198,26 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe) {
     p.z0 = (int32_t)s.z0; p.nzl = s.nzl;
     p.lz_first = L.lz_first;
     p.pair_begin = pb; p.pair_end = pe;
-    p.nit = w->desc.ny / 2 + 1;
+    p.nit = w->desc.ny / 2 + (uint32_t)ns;
     p.key_xy = step_key(w->desc.seed, t, 0);
     p.key_zy = step_key(w->desc.seed, t, 1);
+    p.key_xy2 = step_key(w->desc.seed, t + 1, 0);
+    p.key_zy2 = step_key(w->desc.seed, t + 1, 1);
     const int sk = s.d_skip ? 1 : 0;
     p.skip = s.d_skip; p.last_active = s.d_last_active;
     p.ytile_log2 = YTILE_LOG2; p.ztile_log2 = ZTILE_LOG2; p.nytiles = s.nytiles;
-    p.step_plus1 = (uint32_t)(t + 1);
+    p.step_plus1 = (uint32_t)(t + (uint64_t)ns);
 
     const uint64_t npg = ((uint64_t)(pe - pb) + w->groups - 1) / w->groups;
     const uint64_t total = npg * p.nit;
     // enough warps to fill the machine, but never fewer than ~8 iterations per warp
-    const int bps = s.blocks_per_sm[sk][hoff][todd];
+    const int bps = s.blocks_per_sm[ns - 1][sk][hoff][todd];
     uint64_t max_blocks = (uint64_t)s.num_sms * bps;
     const uint64_t warps_per_block = STEP_THREADS / 32;
     uint64_t want_warps = std::max<uint64_t>(1, total / 8);
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
-    step_fn(w->jidx, (int)hoff, (int)todd, sk)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
+    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
     return FS3D_OK;
@@ -267,7 +277,8 @@ static int exchange_halos(fs3d_world *w) {
     return FS3D_OK;
 }
 
-static int step_once(fs3d_world *w) {
+// one pass over the grid = ns fused SCHEDULE.md steps (ns = 2 needs an even step index)
+static int step_pass(fs3d_world *w, int ns) {
     const int n = (int)w->slabs.size();
     const uint32_t hoff = (uint32_t)((w->step >> 1) & 1);
     if (n == 1) {
@@ -275,7 +286,7 @@ static int step_once(fs3d_world *w) {
         FS3D_CUDA(cudaSetDevice(s.device));
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
-        if (!rc) rc = launch_pairs(w, s, 0, L.npairs);
+        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns);
         if (rc) return rc;
     } else {
         // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
@@ -289,8 +300,8 @@ static int step_once(fs3d_world *w) {
             }
             PairLayout L = pair_layout(s, hoff);
             int rc = launch_skip_map(w, s);
-            if (!rc) rc = launch_pairs(w, s, 0, 1);
-            if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs);
+            if (!rc) rc = launch_pairs(w, s, 0, 1, ns);
+            if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs, ns);
             if (rc) return rc;
             FS3D_CUDA(cudaEventRecord(s.ev_edges, s.s_main));
         }
@@ -299,13 +310,13 @@ static int step_once(fs3d_world *w) {
         for (auto &s : w->slabs) {
             FS3D_CUDA(cudaSetDevice(s.device));
             PairLayout L = pair_layout(s, hoff);
-            if (L.npairs > 2) { rc = launch_pairs(w, s, 1, L.npairs - 1); if (rc) return rc; }
+            if (L.npairs > 2) { rc = launch_pairs(w, s, 1, L.npairs - 1, ns); if (rc) return rc; }
             FS3D_CUDA(cudaEventRecord(s.ev_done, s.s_main));
         }
         w->halo_pending = true;
     }
     w->cur ^= 1;
-    w->step++;
+    w->step += (uint64_t)ns;
     return FS3D_OK;
 }
 
@@ -533,7 +544,14 @@ int fs3d_step(fs3d_world *w, uint32_t n_steps) {
     if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
     if (w->external && w->desc.nz != w->slabs[0].nzl)
         return fail(FS3D_ERR_UNSUPPORTED, "slab worlds step through fs3d_slab_step_* with a caller-driven halo exchange");
-    for (uint32_t i = 0; i < n_steps; ++i) { int rc = step_once(w); if (rc) return rc; }
+    uint32_t left = n_steps;
+    while (left > 0) {
+        // steps 2k and 2k + 1 share the z-pairing and x-offset, so they fuse into one pass
+        const int ns = (left >= 2 && (w->step & 1) == 0 && !(w->desc.flags & FS3D_FLAG_NO_FUSE)) ? 2 : 1;
+        int rc = step_pass(w, ns);
+        if (rc) return rc;
+        left -= (uint32_t)ns;
+    }
     return FS3D_OK;
 }
 
@@ -807,9 +825,10 @@ int fs3d_slab_step_edges(fs3d_world *w) {
     Slab &s = w->slabs[0];
     FS3D_CUDA(cudaSetDevice(s.device));
     PairLayout L = pair_layout(s, (uint32_t)((w->step >> 1) & 1));
+    if (w->pass_ns == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
     int rc = launch_skip_map(w, s);
-    if (!rc) rc = launch_pairs(w, s, 0, 1);
-    if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs);
+    if (!rc) rc = launch_pairs(w, s, 0, 1, w->pass_ns);
+    if (!rc && L.npairs > 1) rc = launch_pairs(w, s, L.npairs - 1, L.npairs, w->pass_ns);
     if (rc) return rc;
     w->edges_phase = 1;
     return FS3D_OK;
@@ -822,7 +841,7 @@ int fs3d_slab_step_interior(fs3d_world *w) {
     Slab &s = w->slabs[0];
     FS3D_CUDA(cudaSetDevice(s.device));
     PairLayout L = pair_layout(s, (uint32_t)((w->step >> 1) & 1));
-    if (L.npairs > 2) { int rc = launch_pairs(w, s, 1, L.npairs - 1); if (rc) return rc; }
+    if (L.npairs > 2) { int rc = launch_pairs(w, s, 1, L.npairs - 1, w->pass_ns); if (rc) return rc; }
     w->edges_phase = 2;
     return FS3D_OK;
 }
@@ -831,8 +850,16 @@ int fs3d_slab_step_finish(fs3d_world *w) {
     if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
     if (w->edges_phase != 2) return fail(FS3D_ERR_INVALID_ARG, "call fs3d_slab_step_interior first");
     w->cur ^= 1;
-    w->step++;
+    w->step += (uint64_t)w->pass_ns;
     w->edges_phase = 0;
+    return FS3D_OK;
+}
+
+int fs3d_slab_pass_steps(fs3d_world *w, uint32_t n_steps) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "a pass fuses 1 or 2 steps");
+    if (w->edges_phase != 0) return fail(FS3D_ERR_INVALID_ARG, "cannot change the pass size inside a pass");
+    w->pass_ns = (int)n_steps;
     return FS3D_OK;
 }
 

@@ -36,8 +36,9 @@ struct StepParams {
     uint32_t nzl;            // owned planes
     uint32_t lz_first;       // local plane index of the left row of pair 0 (0 or 1)
     uint32_t pair_begin, pair_end;   // pairs [begin, end) handled by this launch
-    uint32_t nit;            // march iterations per pair: ny / 2 + 1
+    uint32_t nit;            // march iterations per pair: ny / 2 + NS
     uint32_t key_xy, key_zy; // SCHEDULE.md §3 key(seed, t, axis)
+    uint32_t key_xy2, key_zy2; // keys of step t + 1 (NS = 2 only)
     // settled-tile skipping (SKIP = 1 instantiations only)
     const uint8_t *skip;     // [ztiles][ytiles] 1 = tile provably static this step
     uint32_t *last_active;   // [ztiles][ytiles] (step + 1) of the last enabled block seen in the tile
@@ -62,8 +63,21 @@ template <int J>
 struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u32]
 
 // ---------------------------------------------------------------------------------------------
-template <int J, int OX, int TODD, int SKIP, int THREADS>
+// NS = number of SCHEDULE.md steps fused into this pass (1 or 2).  Two steps can be fused without
+// any halo because hoff = (t >> 1) & 1 is the same for t = 2k and 2k + 1: both steps use the same
+// z-pairing and the same x-offset, so a z-pair of rows is closed under both; only the pipeline
+// along y gets two plane pairs deeper.  NS = 2 requires t even (TODD = 0 for the first step).
+//
+// March, iteration `it` (y1 = 2·it), planes lo = y1 and hi = y1 + 1 freshly loaded:
+//   step t   : sub-step 1 on (hi, lo), sub-step 2 on (lo, prev1)            -> planes y1-1, y1 done
+//   step t+1 : sub-step 3 (ZY) on (prev1, c2), sub-step 4 (XY) on (c2, c3)  -> planes y1-3, y1-2 done
+// carried to the next iteration: prev1 <- hi, c2 <- lo, c3 <- prev1.  A segment that starts above
+// the floor first runs LEAD = 2·NS − 1 iterations without storing to rebuild the carried planes.
+template <int J, int OX, int TODD, int SKIP, int NS, int THREADS>
 __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
+    static_assert(NS == 1 || (NS == 2 && TODD == 0), "a fused pair of steps starts on an even step");
+    constexpr uint32_t LEAD = 2 * NS - 1;      // warm-up iterations to rebuild the carried planes
+    constexpr uint32_t LAG = 2 * NS - 2;       // iteration `it` stores planes 2·it − LAG − 1 and 2·it − LAG
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
@@ -94,14 +108,13 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
         const int32_t zgl = p.z0 + (int32_t)lzl - 1;          // its global z
         bool own[2];
         own[0] = pair_ok && lzl >= 1u && lzl <= p.nzl;
-        own[1] = pair_ok && lzl + 1u >= 1u && lzl + 1u <= p.nzl;
-        // rows beyond the allocation (lzl + 1 > nzl + 1) cannot occur: pairs are enumerated so
-        // that lzl <= nzl, hence lzl + 1 <= nzl + 1 = ghost-high.
+        own[1] = pair_ok && lzl + 1u <= p.nzl;
+        // pairs are enumerated so that lzl <= nzl, hence lzl + 1 <= nzl + 1 = ghost-high.
 
         bool wok[J];                 // this lane's word j exists
         uint32_t xw[J];
         bool hasp[J], hasn[J];
-        uint32_t hxy[J][2], hzy[J];  // linear hash parts
+        uint32_t hxy[J][2], hzy[J];  // linear hash parts (without the key)
         const uint8_t *srow[J][2];
         uint8_t *drow[J][2];
 #pragma unroll
@@ -115,9 +128,9 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                 const size_t off = (size_t)(lzl + r) * plane_rows * row_bytes + (size_t)xw[j] * 32u;
                 srow[j][r] = p.src + off;
                 drow[j][r] = p.dst + off;
-                hxy[j][r] = p.key_xy + xw[j] * HC1 + (uint32_t)(zgl + r) * HC3;
+                hxy[j][r] = xw[j] * HC1 + (uint32_t)(zgl + r) * HC3;
             }
-            hzy[j] = p.key_zy + xw[j] * HC1 + (uint32_t)zgl * HC3;
+            hzy[j] = xw[j] * HC1 + (uint32_t)zgl * HC3;
         }
 
         Raw<J> raw;
@@ -138,18 +151,22 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                     }
         };
 
-        P2 prev[J][2], lo[J][2], hi[J][2];
+        P2 prev1[J][2], c2[J][2], c3[J][2], lo[J][2], hi[J][2];
+        auto reset_carry = [&]() {
 #pragma unroll
-        for (int j = 0; j < J; ++j) { prev[j][0] = {ONES, ONES}; prev[j][1] = {ONES, ONES}; }
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) { prev1[j][r] = {ONES, ONES}; c2[j][r] = {ONES, ONES}; c3[j][r] = {ONES, ONES}; }
+        };
 
         // XY sub-step on (upper, lower) for both rows, upper row is plane yu
-        auto do_xy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu) {
+        auto do_xy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu, uint32_t key) {
             uint32_t en = 0;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 uint32_t rw[J], e[J], ep[J], enx[J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) rw[j] = hash_word(hxy[j][r] + yu * HC2);
+                for (int j = 0; j < J; ++j) rw[j] = hash_word(key + hxy[j][r] + yu * HC2);
                 if (OX == 1) {
 #pragma unroll
                     for (int j = 0; j < J; ++j) e[j] = edge_pack(up[j][r], lw[j][r], rw[j]);
@@ -174,19 +191,21 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
             return en;
         };
         // ZY sub-step across the two rows, upper row is plane yu
-        auto do_zy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu) {
+        auto do_zy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu, uint32_t key) {
             uint32_t en = 0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                uint32_t rw = hash_word(hzy[j] + yu * HC2);
+                uint32_t rw = hash_word(key + hzy[j] + yu * HC2);
                 en |= block_rule(up[j][0], up[j][1], lw[j][0], lw[j][1], rw);
             }
             return en;
         };
 
         // settled-tile bookkeeping (SCHEDULE.md §4): y is cut into blocks of BLK iterations; block b
-        // stores planes 2·BLK·b − 1 … 2·BLK·(b+1) − 2, i.e. y-tile b plus the top plane of tile b − 1
+        // stores planes 2·BLK·b − LAG − 1 … 2·BLK·(b+1) − LAG − 2, i.e. y-tile b plus the top LAG + 1
+        // planes of tile b − 1
         const uint32_t blk_log2 = SKIP ? p.ytile_log2 - 1u : 31u;
+        const uint32_t blk_mask = (1u << blk_log2) - 1u;
         const int32_t ozl = (int32_t)lzl - 1, ozr = (int32_t)lzl;      // owned-plane indices of the two rows
         auto tile_quiet = [&](int32_t oz, uint32_t yt) -> bool {
             if (oz < 0 || oz >= (int32_t)p.nzl || yt >= p.nytiles) return true;
@@ -211,31 +230,26 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
             en_main = 0; en_strad = 0;
         };
 
-        bool have_prev = (it_a == 0);      // prev = STONE below the floor
+        // `it` runs over [it_a, it_b); after a jump (segment start or skipped block) the LEAD
+        // iterations below `it` are replayed without storing (`warm` counts them down)
         bool loaded = false;
         bool next_skip = SKIP ? block_skippable(it_a >> blk_log2) : false;
         uint32_t it = it_a;
+        uint32_t warm = 0;             // > 0: this iteration only rebuilds carried planes
+        bool need_restart = true;
         while (it < it_b) {
-            if (SKIP && next_skip) {       // jump over a provably static block; nothing is read or written
+            if (SKIP && next_skip && warm == 0) {   // jump over a provably static block; nothing is read or written
                 const uint32_t nb = ((it >> blk_log2) + 1u) << blk_log2;
                 it = nb < it_b ? nb : it_b;
-                have_prev = false; loaded = false;
+                need_restart = true; loaded = false;
                 if (it < it_b) next_skip = block_skippable(it >> blk_log2);
                 continue;
             }
-            if (!have_prev) {
-                // lead-in: sub-step 1 of the pair below gives `prev` (plane 2·it − 1, post sub-step 1)
-                load_pair(it - 1);
-#pragma unroll
-                for (int j = 0; j < J; ++j)
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) { lo[j][r] = pack(raw.w[j][r][0]); hi[j][r] = pack(raw.w[j][r][1]); }
-                const uint32_t yl = 2u * (it - 1);
-                if (TODD == 0) do_xy(hi, lo, yl + 1); else do_zy(hi, lo, yl + 1);
-#pragma unroll
-                for (int j = 0; j < J; ++j) { prev[j][0] = hi[j][0]; prev[j][1] = hi[j][1]; }
-                have_prev = true;
-                loaded = false;
+            if (need_restart) {
+                reset_carry();                      // STONE below the floor; harmless garbage otherwise
+                warm = it < LEAD ? it : LEAD;
+                it -= warm;
+                need_restart = false; loaded = false;
             }
             if (!loaded) load_pair(it);
 
@@ -247,34 +261,51 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
 
             // decide about the next iteration now, so that its loads are in flight while we evaluate
             const uint32_t nxt = it + 1;
-            const bool boundary = SKIP && (nxt & ((1u << blk_log2) - 1u)) == 0u;
+            const bool boundary = SKIP && warm == 0 && (nxt & blk_mask) == 0u;
             if (boundary && nxt < it_b) next_skip = block_skippable(nxt >> blk_log2);
             loaded = nxt < it_b && !(boundary && next_skip);
             if (loaded) load_pair(nxt);
 
-            uint32_t e1, e2;
-            if (TODD == 0) { e1 = do_xy(hi, lo, y1 + 1); e2 = do_zy(lo, prev, y1); }
-            else           { e1 = do_zy(hi, lo, y1 + 1); e2 = do_xy(lo, prev, y1); }
-            if (SKIP) {
-                en_main |= e1;
-                if ((it & ((1u << blk_log2) - 1u)) == 0u) en_strad |= e2; else en_main |= e2;
+            uint32_t e1, e2, e3 = 0, e4 = 0;
+            if (TODD == 0) { e1 = do_xy(hi, lo, y1 + 1, p.key_xy); e2 = do_zy(lo, prev1, y1, p.key_zy); }
+            else           { e1 = do_zy(hi, lo, y1 + 1, p.key_zy); e2 = do_xy(lo, prev1, y1, p.key_xy); }
+            if (NS == 2) {   // step t + 1 (odd): ZY with oy = 0 on (y1-1, y1-2), then XY with oy = 1 on (y1-2, y1-3)
+                e3 = do_zy(prev1, c2, y1 - 1u, p.key_zy2);
+                e4 = do_xy(c2, c3, y1 - 2u, p.key_xy2);
+            }
+            if (SKIP && warm == 0) {
+                // enabled blocks seen while storing block b: those of the first LAG/2 + 1 iterations
+                // may lie in tile b − 1
+                if ((it & blk_mask) <= (LAG >> 1)) en_strad |= e1 | e2 | e3 | e4; else en_main |= e1 | e2 | e3 | e4;
             }
 
-            // planes y1 − 1 (prev) and y1 (lo) are final
+            if (warm == 0) {
+                // the two oldest planes are final: NS = 1: (prev1, lo) = y1-1, y1; NS = 2: (c3, c2) = y1-3, y1-2
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (wok[j] && own[r]) {
+                            uint32_t o[8];
+                            const uint32_t ya = y1 - LAG - 1u, yb = y1 - LAG;    // wrap to huge when negative
+                            if (ya < p.ny) { unpack(NS == 2 ? c3[j][r] : prev1[j][r], o); st256(drow[j][r] + (size_t)ya * row_bytes, o); }
+                            if (yb < p.ny) { unpack(NS == 2 ? c2[j][r] : lo[j][r], o);    st256(drow[j][r] + (size_t)yb * row_bytes, o); }
+                        }
+                    }
+            }
 #pragma unroll
             for (int j = 0; j < J; ++j)
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    if (wok[j] && own[r]) {
-                        uint32_t o[8];
-                        if (y1 >= 1u) { unpack(prev[j][r], o); st256(drow[j][r] + (size_t)(y1 - 1) * row_bytes, o); }
-                        if (y1 < p.ny) { unpack(lo[j][r], o);   st256(drow[j][r] + (size_t)y1 * row_bytes, o); }
-                    }
+                    if (NS == 2) { c3[j][r] = prev1[j][r]; c2[j][r] = lo[j][r]; }
+                    prev1[j][r] = hi[j][r];
                 }
-#pragma unroll
-            for (int j = 0; j < J; ++j) { prev[j][0] = hi[j][0]; prev[j][1] = hi[j][1]; }
 
-            if (SKIP && (boundary || nxt >= it_b)) flush_marks(it >> blk_log2);
+            if (warm > 0) {
+                --warm;
+            } else if (SKIP && ((nxt & blk_mask) == 0u || nxt >= it_b)) {
+                flush_marks(it >> blk_log2);
+            }
             it = nxt;
         }
     }

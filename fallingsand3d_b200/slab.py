@@ -80,6 +80,9 @@ class CudaSlabEngine:
     def after_exchange(self):
         self.stream.wait_stream(self.comm_stream)
 
+    def pass_steps(self, ns):
+        self.world.slab_pass_steps(ns)
+
     def step_edges(self):
         self.world.slab_step_edges()
         self.edges_done.record(self.stream)
@@ -119,8 +122,9 @@ class CudaSlabEngine:
 class SlabWorld:
     """The rank-local piece of a global nx×ny×nz world, stepped in lock-step with the other ranks."""
 
-    def __init__(self, nx, ny, nz, seed=1, flags=0, engine_factory=None, group=None):
+    def __init__(self, nx, ny, nz, seed=1, flags=0, engine_factory=None, group=None, fuse=True):
         self.group = group
+        self.fuse = fuse          # steps 2k, 2k+1 share one pass and ONE halo exchange (DESIGN.md §3, §5)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.nx, self.ny, self.nz, self.seed = nx, ny, nz, seed
@@ -170,12 +174,16 @@ class SlabWorld:
         return self.engine.download()
 
     def step(self, n=1):
-        for _ in range(n):
+        left = int(n)
+        while left > 0:
+            ns = 2 if (self.fuse and left >= 2 and self.step_index % 2 == 0) else 1
+            self.engine.pass_steps(ns)
             self.engine.step_edges()        # the two edge planes of the back buffer are final after this
             self.engine.step_interior()     # enqueue first so it overlaps with the exchange below
             self._exchange(back=1)
             self.engine.step_finish()
-            self.step_index += 1
+            self.step_index += ns
+            left -= ns
 
     def sync(self):
         self.engine.sync()

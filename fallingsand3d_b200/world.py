@@ -16,6 +16,7 @@ from . import _lib
 EMPTY, SAND, WATER, STONE = 0, 1, 2, 3
 SCENE_EMPTY, SCENE_SAND_BLOCK, SCENE_MIXED, SCENE_RANDOM, SCENE_MIXED_NOISE = 0, 1, 2, 3, 4
 FLAG_SKIP_SETTLED = 1
+FLAG_NO_FUSE = 2
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
@@ -186,6 +187,9 @@ class VoxelWorld:
         h = _lib.Halo()
         _check(self._lib.fs3d_slab_halo(self._h, int(back), C.byref(h)))
         return h
+
+    def slab_pass_steps(self, n):
+        _check(self._lib.fs3d_slab_pass_steps(self._h, int(n)))
 
     def slab_step_edges(self):
         _check(self._lib.fs3d_slab_step_edges(self._h))

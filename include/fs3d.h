@@ -57,6 +57,7 @@ extern "C" {
 
 /* fs3d_desc.flags */
 #define FS3D_FLAG_SKIP_SETTLED  1u   /* settled-tile skipping (bit-exact; SCHEDULE.md §4) */
+#define FS3D_FLAG_NO_FUSE       2u   /* one kernel pass per step (default: steps 2k, 2k+1 fuse into one pass) */
 
 /* scene ids for fs3d_generate (SCHEDULE.md §5) */
 #define FS3D_SCENE_EMPTY        0
@@ -155,6 +156,8 @@ int  fs3d_raymarch_depth(fs3d_world *w, const fs3d_camera *cam, uint32_t width, 
  *            → fs3d_slab_step_finish (flips buffers, ++step).
  * At a global boundary the ghost plane is STONE and must not be overwritten. */
 int  fs3d_slab_halo(fs3d_world *w, int back, fs3d_halo *out);
+/* Steps fused per pass (1, or 2 when the step index is even): a 2-step pass needs ONE halo exchange. */
+int  fs3d_slab_pass_steps(fs3d_world *w, uint32_t n_steps);
 int  fs3d_slab_step_edges(fs3d_world *w);
 int  fs3d_slab_step_interior(fs3d_world *w);
 int  fs3d_slab_step_finish(fs3d_world *w);

@@ -39,6 +39,10 @@ class OracleSlabEngine:
             b[-1] = STONE
         self.cur = 0
         self.t = 0
+        self.ns = 1
+
+    def pass_steps(self, ns):
+        self.ns = ns
 
     def halo_tensors(self, back):
         b = self.buf[self.cur ^ 1 if back else self.cur]
@@ -54,7 +58,10 @@ class OracleSlabEngine:
         src, dst = self.buf[self.cur], self.buf[self.cur ^ 1]
         ghosts = (dst[0].copy(), dst[-1].copy())
         dst[...] = src
-        self.o.step_range(dst, self.nz, self.zb - 1, self.zb, self.ze, self.seed, self.t)
+        # a fused pass evolves the ghost planes locally for its second step: the (ghost, owned) ZY pair
+        # is closed under steps 2k and 2k + 1, so no exchange is needed in between
+        for k in range(self.ns):
+            self.o.step_range(dst, self.nz, self.zb - 1, self.zb, self.ze, self.seed, self.t + k)
         # the step scribbles on ghost planes; they are refreshed by the exchange (or stay STONE)
         dst[0], dst[-1] = ghosts
         if self.zb == 0:
@@ -67,7 +74,7 @@ class OracleSlabEngine:
 
     def step_finish(self):
         self.cur ^= 1
-        self.t += 1
+        self.t += self.ns
 
     def sync(self):
         pass

@@ -21,36 +21,39 @@ def test_slab_bounds_cover_and_prefer_even_boundaries():
     assert all(lo % 2 == 0 for lo, _ in slab_bounds(250, 4))
 
 
-def _worker(rank, world_size, dims, scene, seed, steps):
+def _worker(rank, world_size, dims, scene, seed, steps, chunk):
     from fallingsand3d_b200.slab import SlabWorld
     nx, ny, nz = dims
     sw = SlabWorld(nx, ny, nz, seed=seed, engine_factory=OracleSlabEngine)
     sw.generate(scene, 4)
     h0 = sw.histogram()
     digests = [sw.digest()]
-    for _ in range(steps):
-        sw.step(1)
+    for _ in range(0, steps, chunk):
+        sw.step(chunk)            # chunk >= 2 takes the fused 2-step passes (one exchange per pass)
         digests.append(sw.digest())
     assert np.array_equal(sw.histogram(), h0)
     whole = sw.gather()
     return digests, whole, [int(v) for v in h0[:4]], sw.exchanges, (sw.z_begin, sw.z_end)
 
 
-@pytest.mark.parametrize("world_size,dims", [(2, (32, 12, 10)), (3, (64, 9, 11)), (2, (32, 8, 3))])
-def test_slab_world_matches_whole_grid_oracle(oracle, world_size, dims):
+@pytest.mark.parametrize("world_size,dims,chunk", [(2, (32, 12, 10), 1), (3, (64, 9, 11), 3), (2, (32, 8, 3), 1),
+                                                   (2, (32, 12, 10), 4), (3, (64, 10, 13), 2)])
+def test_slab_world_matches_whole_grid_oracle(oracle, world_size, dims, chunk):
     nx, ny, nz = dims
-    steps, seed, scene = 9, 21, 3
-    out = run_ranks(world_size, _worker, dims, scene, seed, steps)
+    steps, seed, scene = 12, 21, 3
+    out = run_ranks(world_size, _worker, dims, scene, seed, steps, chunk)
     g = oracle.generate(nx, ny, nz, scene, 4)
     want = [oracle.digest(g)]
     for t in range(steps):
         oracle.step(g, seed, t)
-        want.append(oracle.digest(g))
+        if (t + 1) % chunk == 0:
+            want.append(oracle.digest(g))
+    passes = {1: steps, 2: steps // 2, 3: (steps // 3) * 2, 4: steps // 2}[chunk]   # 3 = a pair + a single
     for rank, (digests, whole, h, exchanges, zr) in enumerate(out):
         assert digests == want, f"rank {rank}"
         assert np.array_equal(whole, g)
         assert h == [int(v) for v in oracle.histogram(oracle.generate(nx, ny, nz, scene, 4))[:4]]
-        assert exchanges == steps + 1          # one per step + the initial refresh
+        assert exchanges == passes + 1         # one per pass + the initial refresh
     assert [o[4] for o in out] == slab_bounds(nz, world_size)
 
 

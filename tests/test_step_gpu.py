@@ -37,7 +37,28 @@ def run_and_compare(fs3d, oracle, nx, ny, nz, scene, seed, steps, every=1, scene
                                   (256, 12, 9), (1024, 6, 5), (1056, 5, 4), (2048, 6, 4), (2080, 4, 3), (4096, 4, 3)])
 def test_small_grids_every_step(fs3d, oracle, dims):
     nx, ny, nz = dims
-    run_and_compare(fs3d, oracle, nx, ny, nz, scene=3, seed=7, steps=12, every=1)
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=3, seed=7, steps=12, every=1)     # single-step passes
+
+
+@pytest.mark.parametrize("dims", [(32, 8, 6), (64, 9, 5), (96, 7, 3), (32, 1, 1), (32, 2, 2), (32, 3, 1),
+                                  (256, 12, 9), (1024, 6, 5), (2048, 6, 4), (2080, 5, 3), (4096, 4, 3)])
+@pytest.mark.parametrize("every", [2, 3, 5])
+def test_small_grids_fused_passes(fs3d, oracle, dims, every):
+    # step(2) = one fused pass; step(3) at even t = pair + single, at odd t = single + pair; ...
+    nx, ny, nz = dims
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=3, seed=7, steps=30, every=every)
+
+
+def test_fused_equals_unfused(fs3d):
+    nx, ny, nz = 256, 96, 40
+    with fs3d.VoxelWorld(nx, ny, nz, seed=5) as a, fs3d.VoxelWorld(nx, ny, nz, seed=5, flags=fs3d.FLAG_NO_FUSE) as b:
+        a.generate(fs3d.SCENE_MIXED_NOISE, 2)
+        b.generate(fs3d.SCENE_MIXED_NOISE, 2)
+        for n in (1, 2, 7, 10, 64):
+            a.step(n)
+            b.step(n)
+            assert a.digest() == b.digest()
+        assert np.array_equal(a.download(), b.download())
 
 
 def test_many_warps_and_segments(fs3d, oracle):
