@@ -255,7 +255,7 @@ def ours(args):
         assert np.array_equal(sw.histogram(), h0), "material counts changed: invalid run"
         digest = sw.digest()
         # kernels per pass per rank: 2 edge launches + 1 interior (NCCL's own kernels not counted); 2 steps per pass
-        launches = 3 * ((K + 1) // 2)
+        launches = (1 if sw.p2p else 3) * ((K + 1) // 2)
 
     value = voxels * K / (ms * 1e-3)
     achieved = 2.0 * voxels * K / (ms * 1e-3) / 1e9 / world_size     # per-GPU algorithmic GB/s
@@ -335,7 +335,8 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"{n}^3 MIXED_NOISE scene (BASELINE configs[3]: 2048^3 mixed sand/water/stone), "
                                f"generated on device, skipping off",
-                   "grid": [n, n, n], "parallelism": f"z-slabs x{world_size}" if world_size > 1 else "single GPU",
+                   "grid": [n, n, n], "parallelism": (f"z-slabs x{world_size}, halo pushed over NVLink peer memory inside the step kernel"
+                                   if world_size > 1 else "single GPU"),
                    "l2": "inputs larger than L2 (grid %.1f GiB per buffer vs 126 MB L2); no flush" % (voxels / 2**30),
                    "digest": hex(digest)},
         "e2e": e2e,

@@ -61,6 +61,9 @@ SIGNATURES = {
     "fs3d_slab_step_edges": (C.c_int, [_W]),
     "fs3d_slab_step_interior": (C.c_int, [_W]),
     "fs3d_slab_step_finish": (C.c_int, [_W]),
+    "fs3d_slab_ipc_export": (C.c_int, [_W, C.c_void_p, C.c_uint64]),
+    "fs3d_slab_ipc_attach": (C.c_int, [_W, C.c_void_p, C.c_void_p]),
+    "fs3d_slab_push_halos": (C.c_int, [_W]),
     "fs3d_last_error": (C.c_char_p, []),
     "fs3d_schedule_version": (C.c_int, []),
 }

@@ -37,7 +37,15 @@ struct Slab {
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
     float *d_palette = nullptr;
     int num_sms = 0;
-    int blocks_per_sm[2][2][2][2] = {};   // [NS-1][SKIP][OX][TODD] for this world's J
+    int blocks_per_sm[2][2][2][2][2] = {};   // [PUSH][NS-1][SKIP][OX][TODD] for this world's J
+    // fused halo push (one process per GPU, CUDA IPC): my arrival counters and the neighbours' memory
+    unsigned long long *d_flags = nullptr;     // [0] iterations delivered from below, [1] from above
+    struct Peer {
+        uint8_t *buf[2] = {nullptr, nullptr};  // neighbour's two slab buffers (IPC-mapped)
+        unsigned long long *flags = nullptr;   // neighbour's d_flags
+        uint32_t nzl = 0;
+        bool valid = false;
+    } peer_lo, peer_hi;
     // settled-tile skipping
     uint8_t *d_skip = nullptr;
     uint32_t *d_last_active = nullptr;
@@ -62,27 +70,29 @@ struct fs3d_world {
     float palette[256 * 4];
     int edges_phase = 0;         // external stepping protocol state
     int pass_ns = 1;             // steps fused in the current external pass
+    bool p2p = false;            // slab world with IPC-attached neighbours: fused halo push, fs3d_step allowed
+    unsigned long long wait_target = 0;   // iterations each neighbour has delivered before the next pass
 };
 
 namespace fs3d {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
 typedef void (*StepFn)(const StepParams);
-#define FS3D_ROW(J, SK) \
-    {{step_kernel<J, 0, 0, SK, 1, STEP_THREADS>, step_kernel<J, 0, 1, SK, 1, STEP_THREADS>}, \
-     {step_kernel<J, 1, 0, SK, 1, STEP_THREADS>, step_kernel<J, 1, 1, SK, 1, STEP_THREADS>}}
-#define FS3D_ROW2(J, SK) {step_kernel<J, 0, 0, SK, 2, STEP_THREADS>, step_kernel<J, 1, 0, SK, 2, STEP_THREADS>}
-// ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even
-static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns) {
-    static StepFn tab1[2][3][2][2] = {
-        {FS3D_ROW(1, 0), FS3D_ROW(2, 0), FS3D_ROW(4, 0)},
-        {FS3D_ROW(1, 1), FS3D_ROW(2, 1), FS3D_ROW(4, 1)},
+#define FS3D_ROW(J, SK, PU) \
+    {{step_kernel<J, 0, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, 0, 1, SK, 1, PU, STEP_THREADS>}, \
+     {step_kernel<J, 1, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, 1, 1, SK, 1, PU, STEP_THREADS>}}
+#define FS3D_ROW2(J, SK, PU) {step_kernel<J, 0, 0, SK, 2, PU, STEP_THREADS>, step_kernel<J, 1, 0, SK, 2, PU, STEP_THREADS>}
+// ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even; push = fused halo push over peer memory
+static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
+    static StepFn tab1[2][2][3][2][2] = {
+        {{FS3D_ROW(1, 0, 0), FS3D_ROW(2, 0, 0), FS3D_ROW(4, 0, 0)}, {FS3D_ROW(1, 1, 0), FS3D_ROW(2, 1, 0), FS3D_ROW(4, 1, 0)}},
+        {{FS3D_ROW(1, 0, 1), FS3D_ROW(2, 0, 1), FS3D_ROW(4, 0, 1)}, {FS3D_ROW(1, 1, 1), FS3D_ROW(2, 1, 1), FS3D_ROW(4, 1, 1)}},
     };
-    static StepFn tab2[2][3][2] = {
-        {FS3D_ROW2(1, 0), FS3D_ROW2(2, 0), FS3D_ROW2(4, 0)},
-        {FS3D_ROW2(1, 1), FS3D_ROW2(2, 1), FS3D_ROW2(4, 1)},
+    static StepFn tab2[2][2][3][2] = {
+        {{FS3D_ROW2(1, 0, 0), FS3D_ROW2(2, 0, 0), FS3D_ROW2(4, 0, 0)}, {FS3D_ROW2(1, 1, 0), FS3D_ROW2(2, 1, 0), FS3D_ROW2(4, 1, 0)}},
+        {{FS3D_ROW2(1, 0, 1), FS3D_ROW2(2, 0, 1), FS3D_ROW2(4, 0, 1)}, {FS3D_ROW2(1, 1, 1), FS3D_ROW2(2, 1, 1), FS3D_ROW2(4, 1, 1)}},
     };
-    return ns == 2 ? tab2[skip][jidx][ox] : tab1[skip][jidx][ox][todd];
+    return ns == 2 ? tab2[push][skip][jidx][ox] : tab1[push][skip][jidx][ox][todd];
 }
 constexpr uint32_t YTILE_LOG2 = 5, ZTILE_LOG2 = 3;   // activity tile = nx x 32 x 8 voxels
 
@@ -111,14 +121,17 @@ static int init_slab(fs3d_world *w, Slab &s) {
     FS3D_CUDA(cudaMalloc(&s.d_scratch, 260 * sizeof(unsigned long long)));
     FS3D_CUDA(cudaMalloc(&s.d_palette, 256 * 4 * sizeof(float)));
     FS3D_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, s.device));
-    for (int ns = 1; ns <= 2; ++ns)
-        for (int sk = 0; sk < 2; ++sk)
-            for (int ox = 0; ox < 2; ++ox)
-                for (int td = 0; td < (ns == 2 ? 1 : 2); ++td) {
-                    int nb = 0;
-                    FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns), STEP_THREADS, 0));
-                    s.blocks_per_sm[ns - 1][sk][ox][td] = std::max(nb, 1);
-                }
+    for (int pu = 0; pu < 2; ++pu)
+        for (int ns = 1; ns <= 2; ++ns)
+            for (int sk = 0; sk < 2; ++sk)
+                for (int ox = 0; ox < 2; ++ox)
+                    for (int td = 0; td < (ns == 2 ? 1 : 2); ++td) {
+                        int nb = 0;
+                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), STEP_THREADS, 0));
+                        s.blocks_per_sm[pu][ns - 1][sk][ox][td] = std::max(nb, 1);
+                    }
+    FS3D_CUDA(cudaMalloc(&s.d_flags, 2 * sizeof(unsigned long long)));
+    FS3D_CUDA(cudaMemsetAsync(s.d_flags, 0, 2 * sizeof(unsigned long long), s.s_main));
     if (w->desc.flags & FS3D_FLAG_SKIP_SETTLED) {
         s.nztiles = (s.nzl + (1u << ZTILE_LOG2) - 1) >> ZTILE_LOG2;
         s.nytiles = (w->desc.ny + (1u << YTILE_LOG2) - 1) >> YTILE_LOG2;
@@ -145,6 +158,12 @@ static void free_slab(Slab &s) {
     if (s.s_main) cudaStreamSynchronize(s.s_main);
     if (s.s_comm) cudaStreamSynchronize(s.s_comm);
     for (int b = 0; b < 2; ++b) if (s.buf[b]) cudaFree(s.buf[b]);
+    for (Slab::Peer *pr : {&s.peer_lo, &s.peer_hi}) {
+        if (!pr->valid) continue;
+        for (int b = 0; b < 2; ++b) if (pr->buf[b]) cudaIpcCloseMemHandle(pr->buf[b]);
+        if (pr->flags) cudaIpcCloseMemHandle(pr->flags);
+    }
+    if (s.d_flags) cudaFree(s.d_flags);
     if (s.d_scratch) cudaFree(s.d_scratch);
     if (s.d_img) cudaFree(s.d_img);
     if (s.d_palette) cudaFree(s.d_palette);
@@ -185,7 +204,7 @@ static PairLayout pair_layout(const Slab &s, uint32_t oz) {
     return L;
 }
 
-static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns) {
+static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns, int push = 0) {
     if (pe <= pb) return FS3D_OK;
     const uint64_t t = w->step;
     const uint32_t hoff = (uint32_t)((t >> 1) & 1), todd = (uint32_t)(t & 1);
@@ -207,17 +226,31 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     p.skip = s.d_skip; p.last_active = s.d_last_active;
     p.ytile_log2 = YTILE_LOG2; p.ztile_log2 = ZTILE_LOG2; p.nytiles = s.nytiles;
     p.step_plus1 = (uint32_t)(t + (uint64_t)ns);
+    if (push) {
+        const size_t pbytes = plane_bytes(w);
+        const int back = w->cur ^ 1;
+        if (s.peer_lo.valid) {
+            p.peer_lo_dst = s.peer_lo.buf[back] + pbytes * ((size_t)s.peer_lo.nzl + 1);
+            p.peer_lo_flag = s.peer_lo.flags + 1;
+        }
+        if (s.peer_hi.valid) {
+            p.peer_hi_dst = s.peer_hi.buf[back];
+            p.peer_hi_flag = s.peer_hi.flags + 0;
+        }
+        p.my_flags = s.d_flags;
+        p.wait_target = w->wait_target;
+    }
 
     const uint64_t npg = ((uint64_t)(pe - pb) + w->groups - 1) / w->groups;
     const uint64_t total = npg * p.nit;
     // enough warps to fill the machine, but never fewer than ~8 iterations per warp
-    const int bps = s.blocks_per_sm[ns - 1][sk][hoff][todd];
+    const int bps = s.blocks_per_sm[push][ns - 1][sk][hoff][todd];
     uint64_t max_blocks = (uint64_t)s.num_sms * bps;
     const uint64_t warps_per_block = STEP_THREADS / 32;
     uint64_t want_warps = std::max<uint64_t>(1, total / 8);
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
-    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
+    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
     return FS3D_OK;
@@ -286,8 +319,9 @@ static int step_pass(fs3d_world *w, int ns) {
         FS3D_CUDA(cudaSetDevice(s.device));
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
-        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns);
+        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, w->p2p ? 1 : 0);
         if (rc) return rc;
+        if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns);   // nit of this pass
     } else {
         // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
         for (auto &s : w->slabs) {
@@ -542,8 +576,9 @@ int fs3d_step_index(fs3d_world *w, uint64_t *out) {
 
 int fs3d_step(fs3d_world *w, uint32_t n_steps) {
     if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
-    if (w->external && w->desc.nz != w->slabs[0].nzl)
-        return fail(FS3D_ERR_UNSUPPORTED, "slab worlds step through fs3d_slab_step_* with a caller-driven halo exchange");
+    if (w->external && w->desc.nz != w->slabs[0].nzl && !w->p2p)
+        return fail(FS3D_ERR_UNSUPPORTED, "slab worlds step through fs3d_slab_step_* with a caller-driven halo exchange, "
+                                          "or through fs3d_step after fs3d_slab_ipc_attach");
     uint32_t left = n_steps;
     while (left > 0) {
         // steps 2k and 2k + 1 share the z-pairing and x-offset, so they fuse into one pass
@@ -860,6 +895,75 @@ int fs3d_slab_pass_steps(fs3d_world *w, uint32_t n_steps) {
     if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "a pass fuses 1 or 2 steps");
     if (w->edges_phase != 0) return fail(FS3D_ERR_INVALID_ARG, "cannot change the pass size inside a pass");
     w->pass_ns = (int)n_steps;
+    return FS3D_OK;
+}
+
+// ---- fused halo push between ranks: CUDA IPC plumbing ---------------------------------------------
+struct IpcBlob {
+    uint32_t magic, nzl, z0, cur;
+    cudaIpcMemHandle_t buf[2];
+    cudaIpcMemHandle_t flags;
+};
+
+int fs3d_slab_ipc_export(fs3d_world *w, void *blob, uint64_t blob_bytes) {
+    if (!w || !blob) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (w->slabs.size() != 1 || !w->external) return fail(FS3D_ERR_UNSUPPORTED, "needs a world made by fs3d_create_slab");
+    if (blob_bytes < sizeof(IpcBlob)) return fail(FS3D_ERR_INVALID_ARG, "blob too small (need FS3D_IPC_BLOB_BYTES)");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    IpcBlob b{};
+    b.magic = 0xF53D1BCu; b.nzl = s.nzl; b.z0 = s.z0; b.cur = (uint32_t)w->cur;
+    for (int i = 0; i < 2; ++i) FS3D_CUDA(cudaIpcGetMemHandle(&b.buf[i], s.buf[i]));
+    FS3D_CUDA(cudaIpcGetMemHandle(&b.flags, s.d_flags));
+    std::memset(blob, 0, (size_t)blob_bytes);
+    std::memcpy(blob, &b, sizeof(b));
+    return FS3D_OK;
+}
+
+static int open_peer(Slab::Peer &pr, const void *blob, uint32_t expect_z, bool expect_end, int my_cur) {
+    IpcBlob b;
+    std::memcpy(&b, blob, sizeof(b));
+    if (b.magic != 0xF53D1BCu) return fail(FS3D_ERR_INVALID_ARG, "not an fs3d IPC blob");
+    if ((expect_end ? b.z0 + b.nzl : b.z0) != expect_z) return fail(FS3D_ERR_INVALID_ARG, "IPC blob is not the adjacent slab");
+    if ((int)b.cur != my_cur) return fail(FS3D_ERR_INVALID_ARG, "neighbour's buffer parity differs (edit worlds collectively)");
+    for (int i = 0; i < 2; ++i)
+        FS3D_CUDA(cudaIpcOpenMemHandle((void **)&pr.buf[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
+    FS3D_CUDA(cudaIpcOpenMemHandle((void **)&pr.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
+    pr.nzl = b.nzl;
+    pr.valid = true;
+    return FS3D_OK;
+}
+
+int fs3d_slab_ipc_attach(fs3d_world *w, const void *lower_blob, const void *upper_blob) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (w->slabs.size() != 1 || !w->external) return fail(FS3D_ERR_UNSUPPORTED, "needs a world made by fs3d_create_slab");
+    if (w->p2p) return fail(FS3D_ERR_INVALID_ARG, "neighbours already attached");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if ((lower_blob != nullptr) != (s.z0 > 0)) return fail(FS3D_ERR_INVALID_ARG, "lower neighbour blob must be given iff z_begin > 0");
+    if ((upper_blob != nullptr) != (s.z0 + s.nzl < w->desc.nz)) return fail(FS3D_ERR_INVALID_ARG, "upper neighbour blob must be given iff z_end < nz");
+    if (lower_blob) { int rc = open_peer(s.peer_lo, lower_blob, s.z0, true, w->cur); if (rc) return rc; }
+    if (upper_blob) { int rc = open_peer(s.peer_hi, upper_blob, s.z0 + s.nzl, false, w->cur); if (rc) return rc; }
+    FS3D_CUDA(cudaMemset(s.d_flags, 0, 2 * sizeof(unsigned long long)));
+    w->wait_target = 0;
+    w->p2p = true;
+    return FS3D_OK;
+}
+
+/* Copies this slab's two edge planes of the FRONT buffer into the neighbours' ghost planes (after
+ * generate / upload / edits).  Every rank calls it, then all ranks barrier before the next step. */
+int fs3d_slab_push_halos(fs3d_world *w) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (!w->p2p) return fail(FS3D_ERR_UNSUPPORTED, "call fs3d_slab_ipc_attach first");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    const size_t pb = plane_bytes(w);
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    if (s.peer_lo.valid)
+        FS3D_CUDA(cudaMemcpyAsync(s.peer_lo.buf[w->cur] + pb * ((size_t)s.peer_lo.nzl + 1), s.buf[w->cur] + pb, pb, cudaMemcpyDefault, s.s_main));
+    if (s.peer_hi.valid)
+        FS3D_CUDA(cudaMemcpyAsync(s.peer_hi.buf[w->cur], s.buf[w->cur] + pb * (size_t)s.nzl, pb, cudaMemcpyDefault, s.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
     return FS3D_OK;
 }
 

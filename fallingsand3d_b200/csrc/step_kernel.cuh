@@ -45,13 +45,35 @@ struct StepParams {
     uint32_t ytile_log2;     // y-tile height = 1 << ytile_log2 planes (>= 2)
     uint32_t ztile_log2;     // z-tile depth = 1 << ztile_log2 owned planes
     uint32_t nytiles;
-    uint32_t step_plus1;     // (uint32)(t + 1)
+    uint32_t step_plus1;     // (uint32)(t + NS)
+    // fused halo push over peer memory (PUSH = 1 instantiations only): the warps that compute this
+    // slab's first / last owned plane also store it into the z-neighbour's ghost plane (its dst
+    // buffer, mapped through CUDA IPC / NVLink) and then add the iterations they finished to the
+    // neighbour's arrival counter; warps that touch a ghost or edge plane first wait until their own
+    // counters show that the neighbours delivered (and stopped reading) the previous pass.
+    uint8_t *peer_lo_dst;                 // neighbour below: its ghost-HIGH plane (dst buffer) or nullptr
+    uint8_t *peer_hi_dst;                 // neighbour above: its ghost-LOW plane (dst buffer) or nullptr
+    unsigned long long *peer_lo_flag;     // neighbour below: its arrive[1]
+    unsigned long long *peer_hi_flag;     // neighbour above: its arrive[0]
+    const unsigned long long *my_flags;   // arrive[0] (from below), arrive[1] (from above)
+    unsigned long long wait_target;       // cumulative iterations the neighbours must have delivered
 };
 
 __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t (&r)[8]) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
+}
+// same, through the coherent path: ghost planes are written by a peer GPU while this kernel runs
+__device__ __forceinline__ void ld256_coherent(const uint8_t *p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void st256(uint8_t *p, const uint32_t (&r)[8]) {
     asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -73,7 +95,7 @@ struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u3
 //   step t+1 : sub-step 3 (ZY) on (prev1, c2), sub-step 4 (XY) on (c2, c3)  -> planes y1-3, y1-2 done
 // carried to the next iteration: prev1 <- hi, c2 <- lo, c3 <- prev1.  A segment that starts above
 // the floor first runs LEAD = 2·NS − 1 iterations without storing to rebuild the carried planes.
-template <int J, int OX, int TODD, int SKIP, int NS, int THREADS>
+template <int J, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
 __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
     static_assert(NS == 1 || (NS == 2 && TODD == 0), "a fused pair of steps starts on an even step");
     constexpr uint32_t LEAD = 2 * NS - 1;      // warm-up iterations to rebuild the carried planes
@@ -133,6 +155,30 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
             hzy[j] = xw[j] * HC1 + (uint32_t)zgl * HC3;
         }
 
+        // fused halo push: which of my two rows is the slab's first / last owned plane
+        uint8_t *plo[J][2], *phi[J][2];
+        bool push_lo = false, push_hi = false;
+        if (PUSH) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const bool is_first = pair_ok && lzl + r == 1u && p.peer_lo_dst != nullptr;
+                const bool is_last = pair_ok && lzl + r == p.nzl && p.peer_hi_dst != nullptr;
+                push_lo = push_lo || is_first;
+                push_hi = push_hi || is_last;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    plo[j][r] = (is_first && wok[j]) ? p.peer_lo_dst + (size_t)xw[j] * 32u : nullptr;
+                    phi[j][r] = (is_last && wok[j]) ? p.peer_hi_dst + (size_t)xw[j] * 32u : nullptr;
+                }
+            }
+            // pairs that read a ghost plane, or write a neighbour's, wait for that neighbour's previous pass
+            const bool near_lo = pair_ok && lzl <= 1u && p.peer_lo_flag != nullptr;
+            const bool near_hi = pair_ok && lzl + 1u >= p.nzl && p.peer_hi_flag != nullptr;
+            if (__any_sync(ONES, near_lo)) while (ld_acquire_sys(p.my_flags + 0) < p.wait_target) __nanosleep(64);
+            if (__any_sync(ONES, near_hi)) while (ld_acquire_sys(p.my_flags + 1) < p.wait_target) __nanosleep(64);
+            __syncwarp();
+        }
+
         Raw<J> raw;
         auto load_pair = [&](uint32_t it) {     // planes y1 = 2·it (lo) and y1 + 1 (hi)
 #pragma unroll
@@ -143,7 +189,8 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t y = 2u * it + h;
                         if (wok[j] && y < p.ny) {
-                            ld256(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
+                            if (PUSH) ld256_coherent(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
+                            else ld256(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) raw.w[j][r][h][q] = 0x03030303u;   // STONE
@@ -288,8 +335,18 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                         if (wok[j] && own[r]) {
                             uint32_t o[8];
                             const uint32_t ya = y1 - LAG - 1u, yb = y1 - LAG;    // wrap to huge when negative
-                            if (ya < p.ny) { unpack(NS == 2 ? c3[j][r] : prev1[j][r], o); st256(drow[j][r] + (size_t)ya * row_bytes, o); }
-                            if (yb < p.ny) { unpack(NS == 2 ? c2[j][r] : lo[j][r], o);    st256(drow[j][r] + (size_t)yb * row_bytes, o); }
+                            if (ya < p.ny) {
+                                unpack(NS == 2 ? c3[j][r] : prev1[j][r], o);
+                                st256(drow[j][r] + (size_t)ya * row_bytes, o);
+                                if (PUSH && plo[j][r]) st256(plo[j][r] + (size_t)ya * row_bytes, o);
+                                if (PUSH && phi[j][r]) st256(phi[j][r] + (size_t)ya * row_bytes, o);
+                            }
+                            if (yb < p.ny) {
+                                unpack(NS == 2 ? c2[j][r] : lo[j][r], o);
+                                st256(drow[j][r] + (size_t)yb * row_bytes, o);
+                                if (PUSH && plo[j][r]) st256(plo[j][r] + (size_t)yb * row_bytes, o);
+                                if (PUSH && phi[j][r]) st256(phi[j][r] + (size_t)yb * row_bytes, o);
+                            }
                         }
                     }
             }
@@ -307,6 +364,15 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                 flush_marks(it >> blk_log2);
             }
             it = nxt;
+        }
+
+        if (PUSH) {
+            // publish: my stores into the neighbour's ghost plane happen-before the counter update
+            if (push_lo || push_hi) __threadfence_system();
+            __syncwarp();
+            const bool leader = pair_ok && xw0 == 0u;      // one lane per z-pair
+            if (leader && push_lo) atomicAdd_system(p.peer_lo_flag, (unsigned long long)(it_b - it_a));
+            if (leader && push_hi) atomicAdd_system(p.peer_hi_flag, (unsigned long long)(it_b - it_a));
         }
     }
 }

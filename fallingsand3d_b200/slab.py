@@ -83,6 +83,15 @@ class CudaSlabEngine:
     def pass_steps(self, ns):
         self.world.slab_pass_steps(ns)
 
+    def ipc_export(self):
+        return self.world.slab_ipc_export()
+
+    def ipc_attach(self, lo, hi):
+        self.world.slab_ipc_attach(lo, hi)
+
+    def push_halos(self):
+        self.world.slab_push_halos()
+
     def step_edges(self):
         self.world.slab_step_edges()
         self.edges_done.record(self.stream)
@@ -122,9 +131,10 @@ class CudaSlabEngine:
 class SlabWorld:
     """The rank-local piece of a global nx×ny×nz world, stepped in lock-step with the other ranks."""
 
-    def __init__(self, nx, ny, nz, seed=1, flags=0, engine_factory=None, group=None, fuse=True):
+    def __init__(self, nx, ny, nz, seed=1, flags=0, engine_factory=None, group=None, fuse=True, p2p=True):
         self.group = group
         self.fuse = fuse          # steps 2k, 2k+1 share one pass and ONE halo exchange (DESIGN.md §3, §5)
+        self.p2p = False          # set below: fused halo push over peer memory instead of NCCL send/recv
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.nx, self.ny, self.nz, self.seed = nx, ny, nz, seed
@@ -137,6 +147,16 @@ class SlabWorld:
             self.engine = engine_factory(nx, ny, nz, seed, self.z_begin, self.z_end)
         self.step_index = 0
         self.exchanges = 0
+        if p2p and fuse and self.world_size > 1 and hasattr(self.engine, "ipc_export"):
+            # plumbing only: swap CUDA IPC handles with the z-neighbours; afterwards the step kernel
+            # itself moves the halos over NVLink (fs3d.h "fused halo push"), no collective per step
+            blobs = [None] * self.world_size
+            dist.all_gather_object(blobs, self.engine.ipc_export(), group=self.group)
+            lo = blobs[self.rank - 1] if self.rank > 0 else None
+            hi = blobs[self.rank + 1] if self.rank + 1 < self.world_size else None
+            self.engine.ipc_attach(lo, hi)
+            dist.barrier(group=self.group)
+            self.p2p = True
 
     # ---- halo exchange of one buffer (back = the buffer the current step is writing) ----
     def _exchange(self, back):
@@ -160,6 +180,11 @@ class SlabWorld:
 
     def refresh_halos(self):
         """After generate/upload/set_cell: make the front buffer's ghost planes current."""
+        if self.p2p:
+            self.engine.push_halos()
+            dist.barrier(group=self.group)
+            self.exchanges += 1
+            return
         self._exchange(back=0)
 
     def generate(self, scene, seed=None):
@@ -174,6 +199,10 @@ class SlabWorld:
         return self.engine.download()
 
     def step(self, n=1):
+        if self.p2p:
+            self.engine.world.step(int(n))      # the library loops; halos move inside the kernels
+            self.step_index += int(n)
+            return
         left = int(n)
         while left > 0:
             ns = 2 if (self.fuse and left >= 2 and self.step_index % 2 == 0) else 1

@@ -188,6 +188,21 @@ class VoxelWorld:
         _check(self._lib.fs3d_slab_halo(self._h, int(back), C.byref(h)))
         return h
 
+    IPC_BLOB_BYTES = 256
+
+    def slab_ipc_export(self):
+        buf = C.create_string_buffer(self.IPC_BLOB_BYTES)
+        _check(self._lib.fs3d_slab_ipc_export(self._h, buf, self.IPC_BLOB_BYTES))
+        return buf.raw
+
+    def slab_ipc_attach(self, lower_blob, upper_blob):
+        lo = C.create_string_buffer(lower_blob, self.IPC_BLOB_BYTES) if lower_blob is not None else None
+        hi = C.create_string_buffer(upper_blob, self.IPC_BLOB_BYTES) if upper_blob is not None else None
+        _check(self._lib.fs3d_slab_ipc_attach(self._h, lo, hi))
+
+    def slab_push_halos(self):
+        _check(self._lib.fs3d_slab_push_halos(self._h))
+
     def slab_pass_steps(self, n):
         _check(self._lib.fs3d_slab_pass_steps(self._h, int(n)))
 

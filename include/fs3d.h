@@ -162,6 +162,20 @@ int  fs3d_slab_step_edges(fs3d_world *w);
 int  fs3d_slab_step_interior(fs3d_world *w);
 int  fs3d_slab_step_finish(fs3d_world *w);
 
+/* ---- fused halo push between ranks over peer memory (CUDA IPC + NVLink) ----
+ * Each rank exports a blob, sends it to its z-neighbours by any means (bench.py: torch.distributed
+ * all_gather_object), and attaches the blobs of the rank below / above (NULL at the global
+ * boundary).  From then on fs3d_step() works on the slab world: ONE kernel per pass computes the
+ * slab, stores its edge planes straight into the neighbours' ghost planes over NVLink and
+ * signals an arrival counter; warps that need a ghost plane wait on their own counter.  No host
+ * synchronisation, no NCCL and no separate edge launches are involved per step.  All ranks must
+ * issue the same sequence of fs3d_step / upload / generate calls; after editing the front buffer
+ * call fs3d_slab_push_halos on every rank and barrier. */
+#define FS3D_IPC_BLOB_BYTES 256
+int  fs3d_slab_ipc_export(fs3d_world *w, void *blob, uint64_t blob_bytes);
+int  fs3d_slab_ipc_attach(fs3d_world *w, const void *lower_blob, const void *upper_blob);
+int  fs3d_slab_push_halos(fs3d_world *w);
+
 const char *fs3d_last_error(void);
 int  fs3d_schedule_version(void);
 

@@ -20,22 +20,38 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for (nx, ny, nz, scene, steps) in [(64, 24, 18, 3, 12), (2048, 32, 24, 4, 10), (256, 256, 256, 2, 40)]:
-        sw = SlabWorld(nx, ny, nz, seed=5)
+    cases = [(64, 24, 18, 3, 12, True), (64, 24, 18, 3, 12, False), (2048, 32, 24, 4, 10, True),
+             (2048, 32, 24, 4, 10, False), (256, 256, 256, 2, 40, True), (4096, 16, 20, 3, 6, True)]
+    for (nx, ny, nz, scene, steps, p2p) in cases:
+        sw = SlabWorld(nx, ny, nz, seed=5, p2p=p2p)
+        assert sw.p2p == p2p
         sw.generate(scene, 3)
         ref = None
         if rank == 0:
             ref = fs3d.VoxelWorld(nx, ny, nz, seed=5)
             ref.generate(scene, 3)
-        for t in range(steps):
-            sw.step(1)
+        t = 0
+        for chunk in [1, 2, 3] * steps:
+            if t >= steps:
+                break
+            sw.step(chunk)
+            t += chunk
             d = sw.digest()
             if rank == 0:
-                ref.step(1)
+                ref.step(chunk)
                 if ref.digest() != d:
                     ok = False
-                    print(f"MISMATCH {nx}x{ny}x{nz} step {t + 1}", flush=True)
+                    print(f"MISMATCH {nx}x{ny}x{nz} p2p={p2p} step {t}", flush=True)
                     break
+        if ok and p2p:
+            # many passes back to back with no host synchronisation in between
+            sw.step(50)
+            d = sw.digest()
+            if rank == 0:
+                ref.step(50)
+                if ref.digest() != d:
+                    ok = False
+                    print(f"MISMATCH {nx}x{ny}x{nz} p2p after 50 async steps", flush=True)
         h = sw.histogram()
         if rank == 0:
             ok = ok and np.array_equal(h, ref.histogram())
