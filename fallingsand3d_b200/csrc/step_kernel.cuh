@@ -124,8 +124,15 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
         const uint32_t it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
         pos += it_b - it_a;
 
-        const uint32_t pair = p.pair_begin + pg * p.groups + g;
+        // PUSH kernels visit the two slab-edge pairs LAST: their warps must wait for the neighbours'
+        // previous pass, and at the end of the kernel that wait has a whole pass of slack, whereas at
+        // the start it would put every bit of inter-GPU skew on the critical path.
+        uint32_t pair = p.pair_begin + pg * p.groups + g;
         const bool pair_ok = lane_ok && pair < p.pair_end;
+        if (PUSH && npairs >= 3u && pair_ok) {
+            const uint32_t pl = pair - p.pair_begin;
+            pair = p.pair_begin + (pl < npairs - 2u ? pl + 1u : (pl == npairs - 2u ? 0u : npairs - 1u));
+        }
         const uint32_t lzl = p.lz_first + 2u * pair;          // local plane of the left row
         const int32_t zgl = p.z0 + (int32_t)lzl - 1;          // its global z
         bool own[2];
