@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfs3d.so")
+LIB_PATH = os.environ.get("FS3D_LIB", os.path.join(HERE, "libfs3d.so"))   # FS3D_LIB: tuning experiments only
 
 
 class Desc(C.Structure):

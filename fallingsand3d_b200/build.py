@@ -10,6 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfs3d.so")
+# tuning experiments: FS3D_NVCC_EXTRA="-DFOO=1" FS3D_LIB_OUT=/path/libfs3d_foo.so python -m fallingsand3d_b200.build --force
 SOURCES = [os.path.join(CSRC, "fs3d.cu")]
 HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "aux_kernels.cuh", "step_kernel.cuh", "raymarch.cuh")] + [
     os.path.join(HERE, "..", "include", "fs3d.h")
@@ -35,12 +36,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    out = os.environ.get("FS3D_LIB_OUT", LIB)
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("FS3D_NVCC_EXTRA", "").split() + ["-o", out] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libfs3d.so")
+    if out != LIB:
+        return out
     with open(os.path.join(HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     return LIB

@@ -6,6 +6,7 @@
 // volume by.  No CPU fallback exists anywhere in this file: without a CUDA device every
 // computing entry point fails with FS3D_ERR_CUDA.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -22,7 +23,10 @@ static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-constexpr int STEP_THREADS = 128;
+#ifndef FS3D_STEP_THREADS
+#define FS3D_STEP_THREADS 256
+#endif
+constexpr int STEP_THREADS = FS3D_STEP_THREADS;
 
 struct Slab {
     int device = 0;
@@ -319,7 +323,8 @@ static int step_pass(fs3d_world *w, int ns) {
         FS3D_CUDA(cudaSetDevice(s.device));
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
-        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, w->p2p ? 1 : 0);
+        static const bool force_push = std::getenv("FS3D_DEBUG_FORCE_PUSH") != nullptr;   // timing experiments only
+        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
         if (rc) return rc;
         if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns);   // nit of this pass
     } else {

@@ -95,8 +95,11 @@ struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u3
 //   step t+1 : sub-step 3 (ZY) on (prev1, c2), sub-step 4 (XY) on (c2, c3)  -> planes y1-3, y1-2 done
 // carried to the next iteration: prev1 <- hi, c2 <- lo, c3 <- prev1.  A segment that starts above
 // the floor first runs LEAD = 2·NS − 1 iterations without storing to rebuild the carried planes.
+#ifndef FS3D_MINB
+#define FS3D_MINB 1
+#endif
 template <int J, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
-__global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel(const StepParams p) {
     static_assert(NS == 1 || (NS == 2 && TODD == 0), "a fused pair of steps starts on an even step");
     constexpr uint32_t LEAD = 2 * NS - 1;      // warm-up iterations to rebuild the carried planes
     constexpr uint32_t LAG = 2 * NS - 2;       // iteration `it` stores planes 2·it − LAG − 1 and 2·it − LAG
@@ -162,22 +165,18 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
             hzy[j] = xw[j] * HC1 + (uint32_t)zgl * HC3;
         }
 
-        // fused halo push: which of my two rows is the slab's first / last owned plane
-        uint8_t *plo[J][2], *phi[J][2];
-        bool push_lo = false, push_hi = false;
+        // fused halo push: which of my two rows (if any) is the slab's first / last owned plane, and
+        // which is a ghost plane (written by a peer GPU while this kernel runs -> coherent loads)
+        int rlo = -1, rhi = -1;
+        bool ghost[2] = {false, false};
+        ptrdiff_t dlo = 0, dhi = 0;    // peer ghost plane address = my dst row address + delta
         if (PUSH) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const bool is_first = pair_ok && lzl + r == 1u && p.peer_lo_dst != nullptr;
-                const bool is_last = pair_ok && lzl + r == p.nzl && p.peer_hi_dst != nullptr;
-                push_lo = push_lo || is_first;
-                push_hi = push_hi || is_last;
-#pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    plo[j][r] = (is_first && wok[j]) ? p.peer_lo_dst + (size_t)xw[j] * 32u : nullptr;
-                    phi[j][r] = (is_last && wok[j]) ? p.peer_hi_dst + (size_t)xw[j] * 32u : nullptr;
-                }
-            }
+            if (pair_ok && p.peer_lo_dst != nullptr) rlo = lzl == 1u ? 0 : (lzl == 0u ? 1 : -1);
+            if (pair_ok && p.peer_hi_dst != nullptr) rhi = lzl == p.nzl ? 0 : (lzl + 1u == p.nzl ? 1 : -1);
+            ghost[0] = lzl == 0u;
+            ghost[1] = lzl + 1u == p.nzl + 1u;
+            dlo = p.peer_lo_dst - (p.dst + (size_t)1u * plane_rows * row_bytes);
+            dhi = p.peer_hi_dst - (p.dst + (size_t)p.nzl * plane_rows * row_bytes);
             // pairs that read a ghost plane, or write a neighbour's, wait for that neighbour's previous pass
             const bool near_lo = pair_ok && lzl <= 1u && p.peer_lo_flag != nullptr;
             const bool near_hi = pair_ok && lzl + 1u >= p.nzl && p.peer_hi_flag != nullptr;
@@ -196,8 +195,11 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t y = 2u * it + h;
                         if (wok[j] && y < p.ny) {
-                            if (PUSH) ld256_coherent(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
-                            else ld256(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
+#ifndef FS3D_EXP_NOCOH
+                            if (PUSH && ghost[r]) ld256_coherent(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
+                            else
+#endif
+                            ld256(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) raw.w[j][r][h][q] = 0x03030303u;   // STONE
@@ -345,14 +347,14 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
                             if (ya < p.ny) {
                                 unpack(NS == 2 ? c3[j][r] : prev1[j][r], o);
                                 st256(drow[j][r] + (size_t)ya * row_bytes, o);
-                                if (PUSH && plo[j][r]) st256(plo[j][r] + (size_t)ya * row_bytes, o);
-                                if (PUSH && phi[j][r]) st256(phi[j][r] + (size_t)ya * row_bytes, o);
+                                if (PUSH && r == rlo) st256(drow[j][r] + (size_t)ya * row_bytes + dlo, o);
+                                if (PUSH && r == rhi) st256(drow[j][r] + (size_t)ya * row_bytes + dhi, o);
                             }
                             if (yb < p.ny) {
                                 unpack(NS == 2 ? c2[j][r] : lo[j][r], o);
                                 st256(drow[j][r] + (size_t)yb * row_bytes, o);
-                                if (PUSH && plo[j][r]) st256(plo[j][r] + (size_t)yb * row_bytes, o);
-                                if (PUSH && phi[j][r]) st256(phi[j][r] + (size_t)yb * row_bytes, o);
+                                if (PUSH && r == rlo) st256(drow[j][r] + (size_t)yb * row_bytes + dlo, o);
+                                if (PUSH && r == rhi) st256(drow[j][r] + (size_t)yb * row_bytes + dhi, o);
                             }
                         }
                     }
@@ -375,6 +377,7 @@ __global__ void __launch_bounds__(THREADS) step_kernel(const StepParams p) {
 
         if (PUSH) {
             // publish: my stores into the neighbour's ghost plane happen-before the counter update
+            const bool push_lo = rlo >= 0, push_hi = rhi >= 0;
             if (push_lo || push_hi) __threadfence_system();
             __syncwarp();
             const bool leader = pair_ok && xw0 == 0u;      // one lane per z-pair
