@@ -26,7 +26,12 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #ifndef FS3D_STEP_THREADS
 #define FS3D_STEP_THREADS 256
 #endif
-constexpr int STEP_THREADS = FS3D_STEP_THREADS;
+constexpr int STEP_THREADS = FS3D_STEP_THREADS;   // J = 1, 2 (nx <= 2048)
+#ifndef FS3D_STEP_THREADS_J4
+#define FS3D_STEP_THREADS_J4 128
+#endif
+constexpr int STEP_THREADS_J4 = FS3D_STEP_THREADS_J4;   // J = 4: 255 registers per thread
+static int step_threads(int jidx) { return jidx == 2 ? STEP_THREADS_J4 : STEP_THREADS; }
 
 struct Slab {
     int device = 0;
@@ -82,10 +87,11 @@ namespace fs3d {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
 typedef void (*StepFn)(const StepParams);
+#define FS3D_TH(J) ((J) == 4 ? STEP_THREADS_J4 : STEP_THREADS)
 #define FS3D_ROW(J, SK, PU) \
-    {{step_kernel<J, 0, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, 0, 1, SK, 1, PU, STEP_THREADS>}, \
-     {step_kernel<J, 1, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, 1, 1, SK, 1, PU, STEP_THREADS>}}
-#define FS3D_ROW2(J, SK, PU) {step_kernel<J, 0, 0, SK, 2, PU, STEP_THREADS>, step_kernel<J, 1, 0, SK, 2, PU, STEP_THREADS>}
+    {{step_kernel<J, 0, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, 0, 1, SK, 1, PU, FS3D_TH(J)>}, \
+     {step_kernel<J, 1, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, 1, 1, SK, 1, PU, FS3D_TH(J)>}}
+#define FS3D_ROW2(J, SK, PU) {step_kernel<J, 0, 0, SK, 2, PU, FS3D_TH(J)>, step_kernel<J, 1, 0, SK, 2, PU, FS3D_TH(J)>}
 // ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even; push = fused halo push over peer memory
 static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
     static StepFn tab1[2][2][3][2][2] = {
@@ -131,7 +137,7 @@ static int init_slab(fs3d_world *w, Slab &s) {
                 for (int ox = 0; ox < 2; ++ox)
                     for (int td = 0; td < (ns == 2 ? 1 : 2); ++td) {
                         int nb = 0;
-                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), STEP_THREADS, 0));
+                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), step_threads(w->jidx), 0));
                         s.blocks_per_sm[pu][ns - 1][sk][ox][td] = std::max(nb, 1);
                     }
     FS3D_CUDA(cudaMalloc(&s.d_flags, 2 * sizeof(unsigned long long)));
@@ -250,11 +256,12 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     // enough warps to fill the machine, but never fewer than ~8 iterations per warp
     const int bps = s.blocks_per_sm[push][ns - 1][sk][hoff][todd];
     uint64_t max_blocks = (uint64_t)s.num_sms * bps;
-    const uint64_t warps_per_block = STEP_THREADS / 32;
+    const int threads = step_threads(w->jidx);
+    const uint64_t warps_per_block = threads / 32;
     uint64_t want_warps = std::max<uint64_t>(1, total / 8);
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
-    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, STEP_THREADS, 0, s.s_main>>>(p);
+    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, 0, s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
     return FS3D_OK;
