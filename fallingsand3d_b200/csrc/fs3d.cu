@@ -42,6 +42,8 @@ struct Slab {
     cudaEvent_t ev_edges = nullptr, ev_done = nullptr;
     cudaEvent_t ev_out_lo = nullptr, ev_out_hi = nullptr;   // my edge plane has landed in the lower / upper neighbour's ghost
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // fs3d_step_host: copies overlap the kernels
+    std::vector<cudaEvent_t> ev_chunk;               // 2 per in-flight chunk (uploaded, computed)
     unsigned long long *d_scratch = nullptr;   // 256 + 1 u64 + 1 u32 flag
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
     float *d_palette = nullptr;
@@ -182,6 +184,9 @@ static void free_slab(Slab &s) {
     if (s.d_tiles_run) cudaFree(s.d_tiles_run);
     cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_out_lo, s.ev_out_hi, s.ev_t0, s.ev_t1};
     for (auto e : evs) if (e) cudaEventDestroy(e);
+    for (auto e : s.ev_chunk) if (e) cudaEventDestroy(e);
+    if (s.s_h2d) cudaStreamDestroy(s.s_h2d);
+    if (s.s_d2h) cudaStreamDestroy(s.s_d2h);
     if (s.s_main) cudaStreamDestroy(s.s_main);
     if (s.s_comm) cudaStreamDestroy(s.s_comm);
     s = Slab();
@@ -907,6 +912,70 @@ int fs3d_slab_pass_steps(fs3d_world *w, uint32_t n_steps) {
     if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "a pass fuses 1 or 2 steps");
     if (w->edges_phase != 0) return fail(FS3D_ERR_INVALID_ARG, "cannot change the pass size inside a pass");
     w->pass_ns = (int)n_steps;
+    return FS3D_OK;
+}
+
+// ---- out-of-core / end-to-end step: host grid in, host grid out, copies overlapped with compute ----
+int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
+    if (!w || !host_in || !host_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host advances 1 or 2 steps per call");
+    if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
+    if (w->slabs.size() != 1 || (w->external && w->desc.nz != w->slabs[0].nzl))
+        return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host needs a single-slab world that holds the whole grid");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if (!s.s_h2d) {
+        FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_h2d, cudaStreamNonBlocking));
+        FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_d2h, cudaStreamNonBlocking));
+    }
+    // A z-pair of planes is closed under a pass, so the grid streams through in chunks
+    // of whole pairs: upload chunk k+1 | step chunk k | download chunk k-1 all overlap.
+    const int ns = (int)n_steps;
+    const uint32_t hoff = (uint32_t)((w->step >> 1) & 1);
+    const PairLayout L = pair_layout(s, hoff);
+    const size_t pb = plane_bytes(w);
+    const uint32_t pairs_per_chunk = std::max<uint32_t>(1, (uint32_t)((256ull << 20) / (2 * pb)));   // ~256 MiB
+    const uint32_t nchunks = (L.npairs + pairs_per_chunk - 1) / pairs_per_chunk;
+    while (s.ev_chunk.size() < 2 * (size_t)nchunks) {
+        cudaEvent_t e;
+        FS3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s.ev_chunk.push_back(e);
+    }
+    uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
+    FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
+    FS3D_CUDA(cudaEventRecord(s.ev_t0, s.s_main));
+    FS3D_CUDA(cudaStreamWaitEvent(s.s_h2d, s.ev_t0, 0));
+    uint8_t *src = s.buf[w->cur], *dst = s.buf[w->cur ^ 1];
+    for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t p0 = c * pairs_per_chunk, p1 = std::min(L.npairs, p0 + pairs_per_chunk);
+        // owned local planes covered by pairs [p0, p1): lz in [lo, hi)
+        uint32_t lo = L.lz_first + 2 * p0, hi = L.lz_first + 2 * p1;
+        lo = std::max(lo, 1u); hi = std::min(hi, s.nzl + 1);
+        const size_t off = pb * lo, bytes = pb * (size_t)(hi - lo);
+        FS3D_CUDA(cudaMemcpyAsync(src + off, host_in + pb * (size_t)(lo - 1), bytes, cudaMemcpyHostToDevice, s.s_h2d));
+        FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
+        FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
+        validate_kernel<<<grid_for(bytes / 16, s), 256, 0, s.s_main>>>(src + off, bytes / 16, flag);
+        FS3D_CUDA(cudaGetLastError());
+        rc = launch_pairs(w, s, p0, p1, ns);
+        if (rc) return rc;
+        FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c + 1], s.s_main));
+        FS3D_CUDA(cudaStreamWaitEvent(s.s_d2h, s.ev_chunk[2 * c + 1], 0));
+        FS3D_CUDA(cudaMemcpyAsync(host_out + pb * (size_t)(lo - 1), dst + off, bytes, cudaMemcpyDeviceToHost, s.s_d2h));
+        w->launches++;   // validate_kernel
+    }
+    uint32_t bad = 0;
+    FS3D_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s.s_d2h));
+    w->cur ^= 1;
+    w->step += (uint64_t)ns;
+    rc = touch_all_tiles(w);
+    if (rc) return rc;
+    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, "host grid contains material codes 4-255 (reserved); the world now holds "
+                                                "undefined cells - upload or generate before stepping again");
     return FS3D_OK;
 }
 

@@ -135,6 +135,16 @@ class VoxelWorld:
         _check(self._lib.fs3d_step_timed(self._h, int(n), C.byref(ms), C.byref(nl)))
         return ms.value, nl.value
 
+    def step_host(self, grid_in, grid_out=None, n=1):
+        """Steps a host-resident grid n (1 or 2) steps: upload, kernels and download overlap chunk by chunk."""
+        if grid_out is None:
+            grid_out = grid_in
+        for g in (grid_in, grid_out):
+            assert g.dtype == np.uint8 and g.flags.c_contiguous and g.shape == self.shape
+        _check(self._lib.fs3d_step_host(self._h, grid_in.ctypes.data_as(C.c_void_p),
+                                        grid_out.ctypes.data_as(C.c_void_p), int(n)))
+        return grid_out
+
     # ---- reductions ----
     def histogram(self):
         h = (C.c_uint64 * 256)()

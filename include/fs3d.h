@@ -131,6 +131,12 @@ int  fs3d_step_index(fs3d_world *w, uint64_t *out);
  * (max over slabs).  kernel_launches, if non-NULL, receives the number of kernels launched. */
 int  fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kernel_launches);
 
+/* End-to-end step for a HOST-resident grid: equivalent to fs3d_upload(host_in); fs3d_step(n);
+ * fs3d_download(host_out) with n = 1 or 2 (2 needs an even step index), but the grid streams
+ * through the GPU in chunks of whole z-pairs so the H2D copy, the kernels and the D2H copy overlap
+ * (use pinned host memory).  host_in may equal host_out.  Single-slab worlds only. */
+int  fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps);
+
 /* ---- reductions (over the planes this world holds; sum across ranks yourself) ---- */
 int  fs3d_histogram(fs3d_world *w, uint64_t counts[256]);
 int  fs3d_digest(fs3d_world *w, uint64_t *out);

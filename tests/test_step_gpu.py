@@ -170,3 +170,34 @@ def test_full_size_properties_1024(fs3d):
 def test_subvolume_of_large_grid_matches_oracle(fs3d, oracle):
     # 2048-wide rows (J = 2 kernel) at full x extent, short in y/z so the oracle finishes in seconds
     run_and_compare(fs3d, oracle, 2048, 96, 24, scene=3, seed=5, steps=16, every=8)
+
+
+@pytest.mark.parametrize("dims", [(64, 40, 30), (2048, 24, 20), (256, 300, 9), (32, 5, 1)])
+def test_step_host_streams_a_host_grid(fs3d, oracle, dims):
+    # fs3d_step_host == upload + step + download, chunked over z-pairs with overlapped copies
+    nx, ny, nz = dims
+    g = oracle.generate(nx, ny, nz, 4, 6)
+    host = g.copy()
+    out = np.empty_like(host)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=11) as w:
+        t = 0
+        for n in (2, 1, 1, 2, 2, 1):          # 2-step calls only on even steps
+            if n == 2 and t % 2:
+                n = 1
+            w.step_host(host, out, n)
+            oracle.run(g, 11, t, n)
+            t += n
+            assert np.array_equal(out, g), f"after step {t}"
+            assert np.array_equal(w.download(), g)      # the device copy is current too
+            assert w.step_index == t
+            host, out = out, host
+        w.step(3)                                        # and ordinary stepping continues from there
+        oracle.run(g, 11, t, 3)
+        assert np.array_equal(w.download(), g)
+        with pytest.raises(fs3d.Fs3dError):
+            w.step_host(host, out, 3)
+        bad = host.copy()
+        bad[0, 0, 0] = 200
+        with pytest.raises(fs3d.Fs3dError) as ei:
+            w.step_host(bad, out, 1)
+        assert ei.value.code == -3
