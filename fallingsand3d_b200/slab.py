@@ -244,5 +244,26 @@ class SlabWorld:
         dist.all_gather_object(outs, local.numpy(), group=self.group)
         return np.concatenate(outs, axis=0)
 
+    def raymarch(self, **cam):
+        """Every rank marches its own slab (fs3d_raymarch_depth); rank 0 keeps, per pixel, the colour of
+        the nearest hit.  Returns the (H, W, 4) uint8 image on rank 0, else None."""
+        img, depth = self.engine.world.raymarch(with_depth=True, **cam)
+        if self.world_size == 1:
+            return img
+        dev = self.engine.reduce_device()
+        timg = torch.from_numpy(img).to(dev)
+        tdep = torch.from_numpy(depth).to(dev)
+        imgs = [torch.empty_like(timg) for _ in range(self.world_size)] if self.rank == 0 else None
+        deps = [torch.empty_like(tdep) for _ in range(self.world_size)] if self.rank == 0 else None
+        dist.gather(timg, imgs, dst=0, group=self.group)
+        dist.gather(tdep, deps, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        d = torch.stack(deps)                       # (ranks, H, W)
+        best = torch.argmin(d, dim=0)               # first minimum: ties cannot differ in colour
+        allimg = torch.stack(imgs)                  # (ranks, H, W, 4)
+        out = torch.gather(allimg, 0, best[None, :, :, None].expand(1, *allimg.shape[1:]))[0]
+        return out.cpu().numpy()
+
     def close(self):
         self.engine.close()

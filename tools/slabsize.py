@@ -1,6 +1,6 @@
 """ad-hoc: time one GPU on a non-cubic grid (nx ny nz) to separate size effects from multi-GPU effects."""
 import sys
-sys.path.insert(0, ".")
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fallingsand3d_b200 as fs3d
 nx, ny, nz = map(int, sys.argv[1:4])
 flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
