@@ -125,18 +125,36 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
     const uint32_t npairs = p.pair_end - p.pair_begin;
     const uint32_t npg = (npairs + p.groups - 1) / p.groups;
     const uint64_t total = (uint64_t)npg * p.nit;
+    // Work split.  Without skipping every iteration costs the same, so the (pair-group x iteration)
+    // space is cut into equal contiguous ranges, one per resident warp (no tail, one lead-in each).
+    // With skipping the live work is concentrated in a few y-bands, so SKIP kernels deal chunks of
+    // CHUNK iterations round-robin to the warps instead (a lead-in per chunk, but balanced).
+    constexpr uint32_t CHUNK = 64;
+    const uint32_t cpp = (p.nit + CHUNK - 1) / CHUNK;            // chunks per pair-group
+    const uint64_t nchunks = (uint64_t)npg * cpp;
+    uint64_t chunk = gw;
     uint64_t pos = total * gw / nw;
     const uint64_t end = total * (gw + 1) / nw;
 
     const size_t row_bytes = p.nx;
     const size_t plane_rows = p.ny;
 
-    while (pos < end) {
-        const uint32_t pg = (uint32_t)(pos / p.nit);
-        const uint32_t it_a = (uint32_t)(pos - (uint64_t)pg * p.nit);
-        const uint64_t left = end - pos;
-        const uint32_t it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
-        pos += it_b - it_a;
+    for (;;) {
+        uint32_t pg, it_a, it_b;
+        if (SKIP) {
+            if (chunk >= nchunks) break;
+            pg = (uint32_t)(chunk / cpp);
+            it_a = (uint32_t)(chunk - (uint64_t)pg * cpp) * CHUNK;
+            it_b = it_a + CHUNK < p.nit ? it_a + CHUNK : p.nit;
+            chunk += nw;
+        } else {
+            if (pos >= end) break;
+            pg = (uint32_t)(pos / p.nit);
+            it_a = (uint32_t)(pos - (uint64_t)pg * p.nit);
+            const uint64_t left = end - pos;
+            it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
+            pos += it_b - it_a;
+        }
 
         // PUSH kernels visit the two slab-edge pairs LAST: their warps must wait for the neighbours'
         // previous pass, and at the end of the kernel that wait has a whole pass of slack, whereas at
