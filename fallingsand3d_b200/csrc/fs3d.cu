@@ -336,7 +336,16 @@ static int step_pass(fs3d_world *w, int ns) {
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
         static const bool force_push = std::getenv("FS3D_DEBUG_FORCE_PUSH") != nullptr;   // timing experiments only
-        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
+        if (w->p2p && w->jidx == 2 && L.npairs >= 3) {
+            // nx > 2048: the J = 4 kernels sit at the 255-register limit and the push code costs them
+            // ~40 % (measured), so only the two edge pairs go through a PUSH launch — first, which
+            // gives the neighbours a whole pass of slack — and the interior through the lean kernel
+            if (!rc) rc = launch_pairs(w, s, 0, 1, ns, 1);
+            if (!rc) rc = launch_pairs(w, s, L.npairs - 1, L.npairs, ns, 1);
+            if (!rc) rc = launch_pairs(w, s, 1, L.npairs - 1, ns, 0);
+        } else {
+            if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
+        }
         if (rc) return rc;
         if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns);   // nit of this pass
     } else {
