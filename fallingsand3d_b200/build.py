@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfs3d.so")
 # tuning experiments: FS3D_NVCC_EXTRA="-DFOO=1" FS3D_LIB_OUT=/path/libfs3d_foo.so python -m fallingsand3d_b200.build --force
 SOURCES = [os.path.join(CSRC, "fs3d.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "aux_kernels.cuh", "step_kernel.cuh", "raymarch.cuh")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "bitslice.cuh", "aux_kernels.cuh", "step_kernel.cuh", "raymarch.cuh")] + [
     os.path.join(HERE, "..", "include", "fs3d.h")
 ]
 

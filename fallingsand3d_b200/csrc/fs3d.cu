@@ -26,12 +26,10 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #ifndef FS3D_STEP_THREADS
 #define FS3D_STEP_THREADS 256
 #endif
-constexpr int STEP_THREADS = FS3D_STEP_THREADS;   // J = 1, 2 (nx <= 2048)
-#ifndef FS3D_STEP_THREADS_J4
-#define FS3D_STEP_THREADS_J4 128
-#endif
-constexpr int STEP_THREADS_J4 = FS3D_STEP_THREADS_J4;   // J = 4: 255 registers per thread
-static int step_threads(int jidx) { return jidx == 2 ? STEP_THREADS_J4 : STEP_THREADS; }
+constexpr int STEP_THREADS = FS3D_STEP_THREADS;
+static int step_threads(int) { return STEP_THREADS; }
+// kernel shapes by row width: jidx 0: J = 1 (nx <= 1024), 1: J = 2 (nx <= 2048), 2: J = 2 x 2 warps (nx <= 4096)
+static uint32_t warps_per_pair(int jidx) { return jidx == 2 ? 2u : 1u; }
 
 struct Slab {
     int device = 0;
@@ -89,20 +87,20 @@ namespace fs3d {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
 typedef void (*StepFn)(const StepParams);
-#define FS3D_TH(J) ((J) == 4 ? STEP_THREADS_J4 : STEP_THREADS)
-#define FS3D_ROW(J, SK, PU) \
-    {{step_kernel<J, 0, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, 0, 1, SK, 1, PU, FS3D_TH(J)>}, \
-     {step_kernel<J, 1, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, 1, 1, SK, 1, PU, FS3D_TH(J)>}}
-#define FS3D_ROW2(J, SK, PU) {step_kernel<J, 0, 0, SK, 2, PU, FS3D_TH(J)>, step_kernel<J, 1, 0, SK, 2, PU, FS3D_TH(J)>}
+#define FS3D_ROW(J, XW, SK, PU) \
+    {{step_kernel<J, XW, 0, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, XW, 0, 1, SK, 1, PU, STEP_THREADS>}, \
+     {step_kernel<J, XW, 1, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, XW, 1, 1, SK, 1, PU, STEP_THREADS>}}
+#define FS3D_ROW2(J, XW, SK, PU) {step_kernel<J, XW, 0, 0, SK, 2, PU, STEP_THREADS>, step_kernel<J, XW, 1, 0, SK, 2, PU, STEP_THREADS>}
+#define FS3D_SHAPES(M, SK, PU) {M(1, 1, SK, PU), M(2, 1, SK, PU), M(2, 2, SK, PU)}
 // ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even; push = fused halo push over peer memory
 static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
     static StepFn tab1[2][2][3][2][2] = {
-        {{FS3D_ROW(1, 0, 0), FS3D_ROW(2, 0, 0), FS3D_ROW(4, 0, 0)}, {FS3D_ROW(1, 1, 0), FS3D_ROW(2, 1, 0), FS3D_ROW(4, 1, 0)}},
-        {{FS3D_ROW(1, 0, 1), FS3D_ROW(2, 0, 1), FS3D_ROW(4, 0, 1)}, {FS3D_ROW(1, 1, 1), FS3D_ROW(2, 1, 1), FS3D_ROW(4, 1, 1)}},
+        {FS3D_SHAPES(FS3D_ROW, 0, 0), FS3D_SHAPES(FS3D_ROW, 1, 0)},
+        {FS3D_SHAPES(FS3D_ROW, 0, 1), FS3D_SHAPES(FS3D_ROW, 1, 1)},
     };
     static StepFn tab2[2][2][3][2] = {
-        {{FS3D_ROW2(1, 0, 0), FS3D_ROW2(2, 0, 0), FS3D_ROW2(4, 0, 0)}, {FS3D_ROW2(1, 1, 0), FS3D_ROW2(2, 1, 0), FS3D_ROW2(4, 1, 0)}},
-        {{FS3D_ROW2(1, 0, 1), FS3D_ROW2(2, 0, 1), FS3D_ROW2(4, 0, 1)}, {FS3D_ROW2(1, 1, 1), FS3D_ROW2(2, 1, 1), FS3D_ROW2(4, 1, 1)}},
+        {FS3D_SHAPES(FS3D_ROW2, 0, 0), FS3D_SHAPES(FS3D_ROW2, 1, 0)},
+        {FS3D_SHAPES(FS3D_ROW2, 0, 1), FS3D_SHAPES(FS3D_ROW2, 1, 1)},
     };
     return ns == 2 ? tab2[push][skip][jidx][ox] : tab1[push][skip][jidx][ox][todd];
 }
@@ -263,7 +261,7 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     uint64_t max_blocks = (uint64_t)s.num_sms * bps;
     const int threads = step_threads(w->jidx);
     const uint64_t warps_per_block = threads / 32;
-    uint64_t want_warps = std::max<uint64_t>(1, total / 8);
+    uint64_t want_warps = std::max<uint64_t>(1, total / 8) * warps_per_pair(w->jidx);
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
     step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, 0, s.s_main>>>(p);
@@ -336,18 +334,10 @@ static int step_pass(fs3d_world *w, int ns) {
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
         static const bool force_push = std::getenv("FS3D_DEBUG_FORCE_PUSH") != nullptr;   // timing experiments only
-        if (w->p2p && w->jidx == 2 && L.npairs >= 3) {
-            // nx > 2048: the J = 4 kernels sit at the 255-register limit and the push code costs them
-            // ~40 % (measured), so only the two edge pairs go through a PUSH launch — first, which
-            // gives the neighbours a whole pass of slack — and the interior through the lean kernel
-            if (!rc) rc = launch_pairs(w, s, 0, 1, ns, 1);
-            if (!rc) rc = launch_pairs(w, s, L.npairs - 1, L.npairs, ns, 1);
-            if (!rc) rc = launch_pairs(w, s, 1, L.npairs - 1, ns, 0);
-        } else {
-            if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
-        }
+        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
         if (rc) return rc;
-        if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns);   // nit of this pass
+        // every warp of an edge pair adds the iterations it finished: nit of this pass x warps per pair
+        if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
     } else {
         // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
         for (auto &s : w->slabs) {

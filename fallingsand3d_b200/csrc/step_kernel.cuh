@@ -64,11 +64,12 @@ __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
-// same, through the coherent path: ghost planes are written by a peer GPU while this kernel runs
+// same, through the coherent path: ghost planes are written by a peer GPU while this kernel runs.
+// (asm volatile statements keep their program order, so these stay behind the acquire of the arrival flag.)
 __device__ __forceinline__ void ld256_coherent(const uint8_t *p, uint32_t (&r)[8]) {
     asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p) : "memory");
+                 : "l"(p));
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
@@ -79,10 +80,6 @@ __device__ __forceinline__ void st256(uint8_t *p, const uint32_t (&r)[8]) {
     asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
-}
-
-__device__ __forceinline__ void prefetch_l2(const uint8_t *p) {
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 
 template <int J>
@@ -102,23 +99,42 @@ struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u3
 #ifndef FS3D_MINB
 #define FS3D_MINB 1
 #endif
-template <int J, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
-__global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel(const StepParams p) {
+//
+// XW = warps per z-pair (1 or 2).  Rows wider than 64 words (nx > 2048) do not fit one warp's registers
+// at J = 4 (255 registers + spills, measured 40 % slower), so two adjacent warps of a CTA share the
+// z-pair instead: warp half h owns words [64h, 64h + 64).  The only thing they exchange is the one
+// edge word per row per XY sub-step that a single warp moves by shuffle.  It goes through one 32-bit
+// shared-memory mailbox per direction, tagged with a sequence number and polled by the consumer.
+// NOT a named barrier: BAR.SYNC also waits for the warp's outstanding global loads, which serialises
+// the register double-buffering (measured 4.15 ms instead of 2.75 ms per pass at 4096 x 4096 x 512).
+template <int J, int XW, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
+__global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepParams p) {
     static_assert(NS == 1 || (NS == 2 && TODD == 0), "a fused pair of steps starts on an even step");
-    // PF = 1 replaces register double-buffering by L2 prefetches two plane pairs ahead.  Measured on
-    // B200 (4096x4096x512, J = 4): 4.06 ms/step vs 2.81 ms with register double-buffering, so it
-    // stays off; kept for experiments (-DFS3D_EXP_PF=1).
-#ifndef FS3D_EXP_PF
-#define FS3D_EXP_PF 0
-#endif
-    constexpr bool PF = (J >= 4) && FS3D_EXP_PF;
+    static_assert(XW == 1 || (XW == 2 && J > 1 && THREADS % 64 == 0), "warp pairs live in one CTA");
+    constexpr bool XCH = XW == 2 && OX == 1;    // edge words cross the warp-pair boundary
     constexpr uint32_t LEAD = 2 * NS - 1;      // warm-up iterations to rebuild the carried planes
     constexpr uint32_t LAG = 2 * NS - 2;       // iteration `it` stores planes 2·it − LAG − 1 and 2·it − LAG
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    // The two warps of a pair are adjacent warps of the CTA (2k, 2k + 1).  Putting them on the same warp
+    // scheduler instead (k, k + THREADS/64) measured 12 % slower (-DFS3D_EXP_PAIR_SPLIT=1).
+#ifndef FS3D_EXP_PAIR_SPLIT
+#define FS3D_EXP_PAIR_SPLIT 0
+#endif
+    constexpr uint32_t PAIRS = XW == 2 ? THREADS / 64 : THREADS / 32;   // work units per CTA
+    const uint32_t wic = threadIdx.x >> 5;        // warp in CTA
+    const uint32_t pic = FS3D_EXP_PAIR_SPLIT ? wic % PAIRS : wic / XW;   // work unit in CTA
+    const uint32_t half = FS3D_EXP_PAIR_SPLIT ? wic / PAIRS : wic % XW;  // which 32·J-word half of the row this warp owns
+    const uint32_t gw = blockIdx.x * PAIRS + pic; // work unit (z-pair marcher): one warp, or a warp pair
+    const uint32_t nw = gridDim.x * PAIRS;
+    __shared__ uint32_t xch_smem[XCH ? PAIRS * 4 : 1];   // [pair in CTA][parity][from half]
+    volatile uint32_t *const xch = xch_smem + (XCH ? pic * 4 : 0);
+    uint32_t xseq = 0;                             // exchanges done; both warps of a pair count alike
+    if (XCH) {
+        if (threadIdx.x < PAIRS * 4) xch_smem[threadIdx.x] = 0u;   // tag 0 is never expected first
+        __syncthreads();
+    }
 
-    uint32_t g = 0, xw0 = lane;
+    uint32_t g = 0, xw0 = lane + half * (32u * J);
     bool lane_ok = true;
     if (J == 1) { g = lane / p.lpr; xw0 = lane - g * p.lpr; lane_ok = g < p.groups; }
 
@@ -187,23 +203,19 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const size_t off = (size_t)(lzl + r) * plane_rows * row_bytes + (size_t)xw[j] * 32u;
-                srow[j][r] = p.src + off;
+                srow[j][r] = p.src + (wok[j] ? off : (size_t)0);   // lanes without a word load (and drop) plane 0
                 drow[j][r] = p.dst + off;
                 hxy[j][r] = xw[j] * HC1 + (uint32_t)(zgl + r) * HC3;
             }
             hzy[j] = xw[j] * HC1 + (uint32_t)zgl * HC3;
         }
 
-        // fused halo push: which of my two rows (if any) is the slab's first / last owned plane, and
-        // which is a ghost plane (written by a peer GPU while this kernel runs -> coherent loads)
+        // fused halo push: which of my two rows (if any) is the slab's first / last owned plane
         int rlo = -1, rhi = -1;
-        bool ghost[2] = {false, false};
         ptrdiff_t dlo = 0, dhi = 0;    // peer ghost plane address = my dst row address + delta
         if (PUSH) {
             if (pair_ok && p.peer_lo_dst != nullptr) rlo = lzl == 1u ? 0 : (lzl == 0u ? 1 : -1);
             if (pair_ok && p.peer_hi_dst != nullptr) rhi = lzl == p.nzl ? 0 : (lzl + 1u == p.nzl ? 1 : -1);
-            ghost[0] = lzl == 0u;
-            ghost[1] = lzl + 1u == p.nzl + 1u;
             dlo = p.peer_lo_dst - (p.dst + (size_t)1u * plane_rows * row_bytes);
             dhi = p.peer_hi_dst - (p.dst + (size_t)p.nzl * plane_rows * row_bytes);
             // pairs that read a ghost plane, or write a neighbour's, wait for that neighbour's previous pass
@@ -214,7 +226,14 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
             __syncwarp();
         }
 
+        // Loads are UNCONDITIONAL (addresses clamped into the buffer) and out-of-grid planes are replaced by
+        // STONE when the words are packed: a predicated load makes the compiler merge its result into
+        // the raw registers right behind the LDG, which waits for the data there and silently turns the
+        // register double-buffering off (seen in SASS; 3.34 ms instead of 2.71 ms per pass).
+        // PUSH kernels read everything through the coherent path (ghost planes are written by a peer GPU
+        // while this kernel runs), one code path and no branch per load.
         Raw<J> raw;
+        const uint32_t ylast = p.ny - 1u;
         auto load_pair = [&](uint32_t it) {     // planes y1 = 2·it (lo) and y1 + 1 (hi)
 #pragma unroll
             for (int j = 0; j < J; ++j)
@@ -223,31 +242,10 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t y = 2u * it + h;
-                        if (wok[j] && y < p.ny) {
-#ifndef FS3D_EXP_NOCOH
-                            if (PUSH && ghost[r]) ld256_coherent(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
-                            else
-#endif
-                            ld256(srow[j][r] + (size_t)y * row_bytes, raw.w[j][r][h]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) raw.w[j][r][h][q] = 0x03030303u;   // STONE
-                        }
+                        const uint8_t *a = srow[j][r] + (size_t)(y < ylast ? y : ylast) * row_bytes;
+                        if (PUSH) ld256_coherent(a, raw.w[j][r][h]);
+                        else ld256(a, raw.w[j][r][h]);
                     }
-        };
-
-        auto prefetch_pair = [&](uint32_t it) {  // one 128 B line per 4 lanes
-            if ((lane & 3u) == 0u) {
-#pragma unroll
-                for (int j = 0; j < J; ++j)
-#pragma unroll
-                    for (int r = 0; r < 2; ++r)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint32_t y = 2u * it + h;
-                            if (wok[j] && y < p.ny) prefetch_l2(srow[j][r] + (size_t)y * row_bytes);
-                        }
-            }
         };
 
         P2 prev1[J][2], c2[J][2], c3[J][2], lo[J][2], hi[J][2];
@@ -261,22 +259,42 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
         // XY sub-step on (upper, lower) for both rows, upper row is plane yu
         auto do_xy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu, uint32_t key) {
             uint32_t en = 0;
+            uint32_t rw[J][2], e[J][2];
+            uint32_t xin[2] = {EDGE_STONE, EDGE_STONE};
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    rw[j][r] = hash_word(key + hxy[j][r] + yu * HC2);
+                    if (OX == 1) e[j][r] = edge_pack(up[j][r], lw[j][r], rw[j][r]);
+                }
+            if (XCH) {
+                // mailbox word = tag(14) | row-1 edge(9) | row-0 edge(9).  Slots alternate by parity: when I
+                // write exchange k + 2 I have seen the partner's k + 1, which it wrote after reading my k.
+                ++xseq;
+                const uint32_t tag = (xseq & 0x3FFFu) << 18;
+                volatile uint32_t *slot = xch + (xseq & 1u) * 2u;
+                const uint32_t mine = half == 0u ? (e[J - 1][0] | (e[J - 1][1] << 9)) : (e[0][0] | (e[0][1] << 9));
+                if (lane == (half == 0u ? 31u : 0u)) slot[half] = tag | mine;
+                uint32_t v;
+                do { v = slot[half ^ 1u]; } while ((v & 0xFFFC0000u) != tag);
+                xin[0] = v & 0x1FFu;
+                xin[1] = (v >> 9) & 0x1FFu;
+            }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                uint32_t rw[J], e[J], ep[J], enx[J];
-#pragma unroll
-                for (int j = 0; j < J; ++j) rw[j] = hash_word(key + hxy[j][r] + yu * HC2);
+                uint32_t ep[J], enx[J];
                 if (OX == 1) {
 #pragma unroll
-                    for (int j = 0; j < J; ++j) e[j] = edge_pack(up[j][r], lw[j][r], rw[j]);
-#pragma unroll
                     for (int j = 0; j < J; ++j) {
-                        uint32_t a = __shfl_up_sync(ONES, e[j], 1);
-                        uint32_t b = __shfl_down_sync(ONES, e[j], 1);
+                        uint32_t a = __shfl_up_sync(ONES, e[j][r], 1);
+                        uint32_t b = __shfl_down_sync(ONES, e[j][r], 1);
                         if (J > 1) {
-                            if (j > 0)     { uint32_t t = __shfl_sync(ONES, e[j - 1], 31); if (lane == 0)  a = t; }
-                            if (j < J - 1) { uint32_t t = __shfl_sync(ONES, e[j + 1], 0);  if (lane == 31) b = t; }
+                            if (j > 0)     { uint32_t t = __shfl_sync(ONES, e[j - 1][r], 31); if (lane == 0)  a = t; }
+                            if (j < J - 1) { uint32_t t = __shfl_sync(ONES, e[j + 1][r], 0);  if (lane == 31) b = t; }
                         }
+                        if (XCH && j == 0     && half == 1u && lane == 0u)  a = xin[r];
+                        if (XCH && j == J - 1 && half == 0u && lane == 31u) b = xin[r];
                         ep[j]  = hasp[j] ? a : EDGE_STONE;
                         enx[j] = hasn[j] ? b : EDGE_STONE;
                     }
@@ -285,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
                     for (int j = 0; j < J; ++j) { ep[j] = EDGE_STONE; enx[j] = EDGE_STONE; }
                 }
 #pragma unroll
-                for (int j = 0; j < J; ++j) en |= xy_substep<OX>(up[j][r], lw[j][r], rw[j], ep[j], enx[j]);
+                for (int j = 0; j < J; ++j) en |= xy_substep<OX>(up[j][r], lw[j][r], rw[j][r], ep[j], enx[j]);
             }
             return en;
         };
@@ -356,15 +374,19 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
 #pragma unroll
             for (int j = 0; j < J; ++j)
 #pragma unroll
-                for (int r = 0; r < 2; ++r) { lo[j][r] = pack(raw.w[j][r][0]); hi[j][r] = pack(raw.w[j][r][1]); }
+                for (int r = 0; r < 2; ++r) {
+                    lo[j][r] = pack(raw.w[j][r][0]);
+                    hi[j][r] = pack(raw.w[j][r][1]);
+                    if (!(wok[j] && y1 < p.ny))      lo[j][r] = {ONES, ONES};   // STONE outside the grid
+                    if (!(wok[j] && y1 + 1u < p.ny)) hi[j][r] = {ONES, ONES};
+                }
 
             // decide about the next iteration now, so that its loads are in flight while we evaluate
             const uint32_t nxt = it + 1;
             const bool boundary = SKIP && warm == 0 && (nxt & blk_mask) == 0u;
             if (boundary && nxt < it_b) next_skip = block_skippable(nxt >> blk_log2);
-            loaded = !PF && nxt < it_b && !(boundary && next_skip);
+            loaded = nxt < it_b && !(boundary && next_skip);
             if (loaded) load_pair(nxt);
-            if (PF && nxt + 1 < it_b) prefetch_pair(nxt + 1);
 
             uint32_t e1, e2, e3 = 0, e4 = 0;
             if (TODD == 0) { e1 = do_xy(hi, lo, y1 + 1, p.key_xy); e2 = do_zy(lo, prev1, y1, p.key_zy); }
@@ -424,7 +446,7 @@ __global__ void __launch_bounds__(THREADS, (J <= 2 ? FS3D_MINB : 1)) step_kernel
             const bool push_lo = rlo >= 0, push_hi = rhi >= 0;
             if (push_lo || push_hi) __threadfence_system();
             __syncwarp();
-            const bool leader = pair_ok && xw0 == 0u;      // one lane per z-pair
+            const bool leader = pair_ok && xw0 == half * (32u * J);   // one lane per z-pair and warp (XW adds per pair)
             if (leader && push_lo) atomicAdd_system(p.peer_lo_flag, (unsigned long long)(it_b - it_a));
             if (leader && push_hi) atomicAdd_system(p.peer_hi_flag, (unsigned long long)(it_b - it_a));
         }

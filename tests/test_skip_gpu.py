@@ -24,7 +24,8 @@ def test_skip_is_bit_exact_while_a_sand_block_settles(fs3d, oracle):
         assert fractions[-1] == 0.0           # the settled pile costs nothing
 
 
-@pytest.mark.parametrize("dims,scene,steps", [((128, 100, 40), 2, 300), ((2048, 70, 20), 4, 120), ((96, 33, 17), 3, 150)])
+@pytest.mark.parametrize("dims,scene,steps", [((128, 100, 40), 2, 300), ((2048, 70, 20), 4, 120), ((96, 33, 17), 3, 150),
+                                              ((4096, 70, 12), 4, 60)])
 def test_skip_on_equals_skip_off(fs3d, dims, scene, steps):
     nx, ny, nz = dims
     with fs3d.VoxelWorld(nx, ny, nz, seed=3) as a, fs3d.VoxelWorld(nx, ny, nz, seed=3, flags=fs3d.FLAG_SKIP_SETTLED) as b:

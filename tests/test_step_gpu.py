@@ -31,17 +31,18 @@ def run_and_compare(fs3d, oracle, nx, ny, nz, scene, seed, steps, every=1, scene
         assert np.array_equal(w.histogram(), oracle.histogram(g))
 
 
-# every kernel instantiation: J=1 with row groups (nx < 1024), J=1 full warp, J=2, J=4;
-# odd/even ny and nz; ny, nz = 1
+# every kernel instantiation: J=1 with row groups (nx < 1024), J=1 full warp, J=2, J=2 x warp pair
+# (nx > 2048: full, half-empty second warp, one word in the second warp); odd/even ny and nz; ny, nz = 1
 @pytest.mark.parametrize("dims", [(32, 8, 6), (64, 9, 5), (96, 7, 3), (128, 16, 4), (32, 1, 1), (32, 2, 1), (32, 1, 2),
-                                  (256, 12, 9), (1024, 6, 5), (1056, 5, 4), (2048, 6, 4), (2080, 4, 3), (4096, 4, 3)])
+                                  (256, 12, 9), (1024, 6, 5), (1056, 5, 4), (2048, 6, 4), (2080, 4, 3), (4096, 4, 3),
+                                  (3072, 5, 4), (4064, 3, 2)])
 def test_small_grids_every_step(fs3d, oracle, dims):
     nx, ny, nz = dims
     run_and_compare(fs3d, oracle, nx, ny, nz, scene=3, seed=7, steps=12, every=1)     # single-step passes
 
 
 @pytest.mark.parametrize("dims", [(32, 8, 6), (64, 9, 5), (96, 7, 3), (32, 1, 1), (32, 2, 2), (32, 3, 1),
-                                  (256, 12, 9), (1024, 6, 5), (2048, 6, 4), (2080, 5, 3), (4096, 4, 3)])
+                                  (256, 12, 9), (1024, 6, 5), (2048, 6, 4), (2080, 5, 3), (4096, 4, 3), (3104, 6, 5)])
 @pytest.mark.parametrize("every", [2, 3, 5])
 def test_small_grids_fused_passes(fs3d, oracle, dims, every):
     # step(2) = one fused pass; step(3) at even t = pair + single, at odd t = single + pair; ...
@@ -65,6 +66,8 @@ def test_many_warps_and_segments(fs3d, oracle):
     # enough rows that warps split marches into segments with lead-ins
     run_and_compare(fs3d, oracle, 64, 200, 40, scene=3, seed=3, steps=8, every=2)
     run_and_compare(fs3d, oracle, 2048, 64, 10, scene=4, seed=4, steps=8, every=4)
+    # warp pairs (nx > 2048): many pairs per CTA, segments starting mid-march, both x-offsets
+    run_and_compare(fs3d, oracle, 4096, 72, 14, scene=3, seed=9, steps=8, every=3)
 
 
 def test_config1_64cubed_sand_block_500_steps(fs3d, oracle):
