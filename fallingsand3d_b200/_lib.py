@@ -65,6 +65,12 @@ SIGNATURES = {
     "fs3d_slab_ipc_export": (C.c_int, [_W, C.c_void_p, C.c_uint64]),
     "fs3d_slab_ipc_attach": (C.c_int, [_W, C.c_void_p, C.c_void_p]),
     "fs3d_slab_push_halos": (C.c_int, [_W]),
+    "fs3d_frame_export": (C.c_int, [_W, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "fs3d_frame_attach": (C.c_int, [_W, C.c_void_p, C.c_uint32]),
+    "fs3d_raymarch_to_frame": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32]),
+    "fs3d_frame_resolve": (C.c_int, [_W, C.c_void_p]),
+    "fs3d_save": (C.c_int, [_W, C.c_char_p]),
+    "fs3d_load": (C.c_int, [_W, C.c_char_p]),
     "fs3d_last_error": (C.c_char_p, []),
     "fs3d_schedule_version": (C.c_int, []),
 }

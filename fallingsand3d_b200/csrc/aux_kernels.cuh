@@ -142,6 +142,34 @@ __global__ void digest_kernel(const uint8_t *p, uint64_t n16, uint64_t base, uns
     if ((threadIdx.x & 31) == 0 && sum) atomicAdd(out, (unsigned long long)sum);
 }
 
+// checkpoint payload (fs3d.h "checkpoint"): 4 voxels per byte, voxel i of the stream in bits 2(i & 3) of byte i >> 2.
+// One thread packs 16 voxels (one uint4) into one uint32 / unpacks one uint32 into a uint4.
+__global__ void pack2_kernel(const uint8_t *cells, uint64_t n16, uint32_t *packed) {
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n16; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 q = reinterpret_cast<const uint4 *>(cells)[v];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = (w[k] & 3u) | (((w[k] >> 8) & 3u) << 2) | (((w[k] >> 16) & 3u) << 4) | (((w[k] >> 24) & 3u) << 6);
+            out |= b << (8 * k);
+        }
+        packed[v] = out;
+    }
+}
+__global__ void unpack2_kernel(const uint32_t *packed, uint64_t n16, uint8_t *cells) {
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n16; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t in = packed[v];
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = (in >> (8 * k)) & 0xFFu;
+            w[k] = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | (((b >> 6) & 3u) << 24);
+        }
+        reinterpret_cast<uint4 *>(cells)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // fill the part of a global box that lies in this slab; owned = local plane 1
 __global__ void fill_box_kernel(uint8_t *owned, uint32_t nx, uint32_t ny, uint32_t z0, uint32_t nzl,
                                 uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t zb0, uint32_t zb1, uint8_t m) {

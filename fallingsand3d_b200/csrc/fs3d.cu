@@ -6,6 +6,7 @@
 // volume by.  No CPU fallback exists anywhere in this file: without a CUDA device every
 // computing entry point fails with FS3D_ERR_CUDA.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -55,10 +56,18 @@ struct Slab {
         uint32_t nzl = 0;
         bool valid = false;
     } peer_lo, peer_hi;
+    // fused multi-rank ray-march: the compositor's frame (one slot of W x H 64-bit words per rank)
+    struct Frame {
+        unsigned long long *base = nullptr;   // slot 0; mine if `owner`, else the compositor's memory mapped through CUDA IPC
+        bool owner = false;
+        uint32_t width = 0, height = 0, nslots = 0, slot = 0;
+        uint32_t *d_rgba = nullptr;           // compositor only: resolved image
+    } frame;
     // settled-tile skipping
     uint8_t *d_skip = nullptr;
     uint32_t *d_last_active = nullptr;
     unsigned long long *d_tiles_run = nullptr;
+    uint32_t *d_runs = nullptr, *d_nruns = nullptr;   // live march segments of the launch in flight
     uint32_t nztiles = 0, nytiles = 0;
 };
 
@@ -149,6 +158,9 @@ static int init_slab(fs3d_world *w, Slab &s) {
         FS3D_CUDA(cudaMalloc(&s.d_skip, nt));
         FS3D_CUDA(cudaMalloc(&s.d_last_active, nt * sizeof(uint32_t)));
         FS3D_CUDA(cudaMalloc(&s.d_tiles_run, 2 * sizeof(unsigned long long)));
+        const size_t max_runs = ((size_t)s.nzl / 2 + 2) * (((size_t)w->desc.ny / 2 + 2) / (1u << (YTILE_LOG2 - 1)) + 2);
+        FS3D_CUDA(cudaMalloc(&s.d_runs, max_runs * 3 * sizeof(uint32_t)));
+        FS3D_CUDA(cudaMalloc(&s.d_nruns, sizeof(uint32_t)));
         FS3D_CUDA(cudaMemsetAsync(s.d_skip, 0, nt, s.s_main));
         FS3D_CUDA(cudaMemsetAsync(s.d_last_active, 0, nt * sizeof(uint32_t), s.s_main));
         FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, 2 * sizeof(unsigned long long), s.s_main));
@@ -173,6 +185,8 @@ static void free_slab(Slab &s) {
         for (int b = 0; b < 2; ++b) if (pr->buf[b]) cudaIpcCloseMemHandle(pr->buf[b]);
         if (pr->flags) cudaIpcCloseMemHandle(pr->flags);
     }
+    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else cudaIpcCloseMemHandle(s.frame.base); }
+    if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
     if (s.d_flags) cudaFree(s.d_flags);
     if (s.d_scratch) cudaFree(s.d_scratch);
     if (s.d_img) cudaFree(s.d_img);
@@ -180,6 +194,8 @@ static void free_slab(Slab &s) {
     if (s.d_skip) cudaFree(s.d_skip);
     if (s.d_last_active) cudaFree(s.d_last_active);
     if (s.d_tiles_run) cudaFree(s.d_tiles_run);
+    if (s.d_runs) cudaFree(s.d_runs);
+    if (s.d_nruns) cudaFree(s.d_nruns);
     cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_out_lo, s.ev_out_hi, s.ev_t0, s.ev_t1};
     for (auto e : evs) if (e) cudaEventDestroy(e);
     for (auto e : s.ev_chunk) if (e) cudaEventDestroy(e);
@@ -264,6 +280,17 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     uint64_t want_warps = std::max<uint64_t>(1, total / 8) * warps_per_pair(w->jidx);
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
+    if (sk) {
+        // compact the live (pair group, y-block) segments of this launch into the run list the warps share out
+        const uint32_t units = (uint32_t)(blocks * warps_per_block / warps_per_pair(w->jidx));
+        FS3D_CUDA(cudaMemsetAsync(s.d_nruns, 0, sizeof(uint32_t), s.s_main));
+        skip_runs_kernel<<<(unsigned)((npg + 3) / 4), 128, 0, s.s_main>>>(
+            s.d_skip, s.nytiles, ZTILE_LOG2, YTILE_LOG2 - 1, s.nzl, L.lz_first, pb, pe, w->groups, p.nit, units,
+            s.d_tiles_run, s.d_runs, s.d_nruns);
+        FS3D_CUDA(cudaGetLastError());
+        w->launches++;
+        p.runs = s.d_runs; p.nruns = s.d_nruns;
+    }
     step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, 0, s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
@@ -417,7 +444,7 @@ static unsigned grid_for(uint64_t n, const Slab &s) {
 
 // ---- raymarch host side ----------------------------------------------------------------------------
 int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode,
-                   uint8_t *host_rgba8, float *host_depth) {
+                   uint8_t *host_rgba8, float *host_depth, unsigned long long *frame_slot) {
     if ((int)w->slabs.size() > RM_MAX_SLABS) return fail(FS3D_ERR_UNSUPPORTED, "too many slabs for raymarch");
     if ((mode & 15u) > FS3D_RM_VOXELS) return fail(FS3D_ERR_INVALID_ARG, "unknown raymarch mode");
     Slab &s0 = w->slabs[0];
@@ -474,10 +501,12 @@ int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32
     }
     p.img = s0.d_img;
     p.depth = d_depth;
+    p.frame = frame_slot;
     dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
     raymarch_kernel<<<grd, blk, 0, s0.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
+    if (frame_slot) return FS3D_OK;   // asynchronous: the pixels went straight into the compositor's frame
     FS3D_CUDA(cudaMemcpyAsync(host_rgba8, s0.d_img, npix * 4, cudaMemcpyDeviceToHost, s0.s_main));
     if (host_depth) FS3D_CUDA(cudaMemcpyAsync(host_depth, d_depth, npix * sizeof(float), cudaMemcpyDeviceToHost, s0.s_main));
     FS3D_CUDA(cudaStreamSynchronize(s0.s_main));
@@ -944,6 +973,10 @@ int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uin
     }
     uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
     FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
+    if (s.d_skip) {   // the grid comes from the host: nothing is known to be static
+        FS3D_CUDA(cudaMemsetAsync(s.d_skip, 0, (size_t)s.nztiles * s.nytiles, s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, 2 * sizeof(unsigned long long), s.s_main));
+    }
     FS3D_CUDA(cudaEventRecord(s.ev_t0, s.s_main));
     FS3D_CUDA(cudaStreamWaitEvent(s.s_h2d, s.ev_t0, 0));
     uint8_t *src = s.buf[w->cur], *dst = s.buf[w->cur ^ 1];
@@ -1045,6 +1078,205 @@ int fs3d_slab_push_halos(fs3d_world *w) {
         FS3D_CUDA(cudaMemcpyAsync(s.peer_hi.buf[w->cur], s.buf[w->cur] + pb * (size_t)s.nzl, pb, cudaMemcpyDefault, s.s_main));
     FS3D_CUDA(cudaStreamSynchronize(s.s_main));
     return FS3D_OK;
+}
+
+// ---- fused multi-rank ray-march: every rank's kernel stores into the compositor's frame over NVLink ----
+struct FrameBlob {
+    uint32_t magic, width, height, nslots;
+    cudaIpcMemHandle_t mem;
+};
+
+int fs3d_frame_export(fs3d_world *w, uint32_t width, uint32_t height, uint32_t n_slots, void *blob, uint64_t blob_bytes) {
+    if (!w || !blob) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (width == 0 || height == 0 || width > 16384 || height > 16384 || n_slots == 0 || n_slots > 64)
+        return fail(FS3D_ERR_INVALID_ARG, "bad frame size");
+    if (blob_bytes < sizeof(FrameBlob)) return fail(FS3D_ERR_INVALID_ARG, "blob too small (need FS3D_IPC_BLOB_BYTES)");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    int rc = sync_all(w);
+    if (rc) return rc;
+    if (s.frame.base) {
+        if (s.frame.owner) cudaFree(s.frame.base); else cudaIpcCloseMemHandle(s.frame.base);
+        if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
+        s.frame = Slab::Frame();
+    }
+    const size_t npix = (size_t)width * height;
+    FS3D_CUDA(cudaMalloc(&s.frame.base, npix * n_slots * sizeof(unsigned long long)));
+    s.frame.owner = true;
+    FS3D_CUDA(cudaMalloc(&s.frame.d_rgba, npix * sizeof(uint32_t)));
+    FS3D_CUDA(cudaMemset(s.frame.base, 0xFF, npix * n_slots * sizeof(unsigned long long)));   // every slot: all misses
+    s.frame.width = width; s.frame.height = height; s.frame.nslots = n_slots; s.frame.slot = 0;
+    FrameBlob b{};
+    b.magic = 0xF53DF4A3u; b.width = width; b.height = height; b.nslots = n_slots;
+    FS3D_CUDA(cudaIpcGetMemHandle(&b.mem, s.frame.base));
+    std::memset(blob, 0, (size_t)blob_bytes);
+    std::memcpy(blob, &b, sizeof(b));
+    return FS3D_OK;
+}
+
+int fs3d_frame_attach(fs3d_world *w, const void *blob, uint32_t slot) {
+    if (!w || !blob) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    FrameBlob b;
+    std::memcpy(&b, blob, sizeof(b));
+    if (b.magic != 0xF53DF4A3u) return fail(FS3D_ERR_INVALID_ARG, "not an fs3d frame blob");
+    if (slot >= b.nslots) return fail(FS3D_ERR_OUT_OF_RANGE, "slot outside the frame");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if (s.frame.owner) {   // the compositor attaches to its own frame: only the slot changes
+        if (b.width != s.frame.width || b.height != s.frame.height || b.nslots != s.frame.nslots)
+            return fail(FS3D_ERR_INVALID_ARG, "blob does not describe this world's frame");
+        s.frame.slot = slot;
+        return FS3D_OK;
+    }
+    if (s.frame.base) { cudaIpcCloseMemHandle(s.frame.base); s.frame = Slab::Frame(); }
+    FS3D_CUDA(cudaIpcOpenMemHandle((void **)&s.frame.base, b.mem, cudaIpcMemLazyEnablePeerAccess));
+    s.frame.width = b.width; s.frame.height = b.height; s.frame.nslots = b.nslots; s.frame.slot = slot;
+    return FS3D_OK;
+}
+
+int fs3d_raymarch_to_frame(fs3d_world *w, const fs3d_camera *cam, uint32_t mode) {
+    if (!w || !cam) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    Slab &s = w->slabs[0];
+    if (!s.frame.base) return fail(FS3D_ERR_UNSUPPORTED, "call fs3d_frame_export / fs3d_frame_attach first");
+    const size_t npix = (size_t)s.frame.width * s.frame.height;
+    return raymarch_world(w, cam, s.frame.width, s.frame.height, mode, nullptr, nullptr, s.frame.base + npix * s.frame.slot);
+}
+
+int fs3d_frame_resolve(fs3d_world *w, uint8_t *host_rgba8) {
+    if (!w || !host_rgba8) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    Slab &s = w->slabs[0];
+    if (!s.frame.base || !s.frame.owner) return fail(FS3D_ERR_UNSUPPORTED, "only the rank that called fs3d_frame_export resolves");
+    FS3D_CUDA(cudaSetDevice(s.device));
+    const size_t npix = (size_t)s.frame.width * s.frame.height;
+    frame_resolve_kernel<<<grid_for(npix, s), 256, 0, s.s_main>>>(s.frame.base, s.frame.nslots, npix, s.frame.d_rgba);
+    FS3D_CUDA(cudaGetLastError());
+    w->launches++;
+    FS3D_CUDA(cudaMemcpyAsync(host_rgba8, s.frame.d_rgba, npix * 4, cudaMemcpyDeviceToHost, s.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    return FS3D_OK;
+}
+
+// ---- checkpoint: the planes this world holds + step index + seed, 2 bits per voxel ----------------
+struct CkptHeader {
+    char     magic[8];            // "FS3DCKPT"
+    uint32_t format_version;      // FS3D_CKPT_VERSION
+    uint32_t schedule_version;    // FS3D_SCHEDULE_VERSION the state was produced under
+    uint32_t nx, ny, nz;          // global grid
+    uint32_t z_begin, z_end;      // planes in this file
+    uint32_t encoding;            // 1 = 2-bit packed, x fastest
+    uint64_t step, seed;
+    uint64_t digest;              // fs3d_digest of these planes (global indices): checked on load
+    uint64_t payload_bytes;
+    uint64_t reserved;
+};
+static_assert(sizeof(CkptHeader) == FS3D_CKPT_HEADER_BYTES, "checkpoint header layout is part of the file format");
+
+int fs3d_save(fs3d_world *w, const char *path) {
+    if (!w || !path) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    uint64_t dg = 0;
+    int rc = fs3d_digest(w, &dg);          // also synchronises
+    if (rc) return rc;
+    const size_t pb = plane_bytes(w);
+    const uint32_t zb = w->slabs.front().z0, ze = w->slabs.back().z0 + w->slabs.back().nzl;
+    CkptHeader h{};
+    std::memcpy(h.magic, "FS3DCKPT", 8);
+    h.format_version = FS3D_CKPT_VERSION; h.schedule_version = FS3D_SCHEDULE_VERSION;
+    h.nx = w->desc.nx; h.ny = w->desc.ny; h.nz = w->desc.nz; h.z_begin = zb; h.z_end = ze;
+    h.encoding = 1; h.step = w->step; h.seed = w->desc.seed; h.digest = dg;
+    h.payload_bytes = pb / 4 * (uint64_t)(ze - zb);      // nx % 32 == 0, so a plane packs to whole bytes
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path + " for writing");
+    bool io_ok = std::fwrite(&h, sizeof(h), 1, f) == 1;
+    // pack on the device, stream to the file in chunks of whole planes (<= ~64 MiB packed)
+    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / 4));
+    std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / 4));
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        uint32_t *d_packed = nullptr;
+        const uint32_t cp = std::min(planes_per_chunk, s.nzl);
+        cudaError_t e = cudaMalloc(&d_packed, (size_t)cp * (pb / 4));
+        if (e != cudaSuccess) { std::fclose(f); FS3D_CUDA(e); }
+        for (uint32_t z = 0; z < s.nzl && io_ok; z += cp) {
+            const uint32_t n = std::min(cp, s.nzl - z);
+            const uint64_t n16 = pb * n / 16;
+            pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur) + pb * z, n16, d_packed);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_packed, n16 * 4, cudaMemcpyDeviceToHost, s.s_main);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
+            if (e != cudaSuccess) { cudaFree(d_packed); std::fclose(f); FS3D_CUDA(e); }
+            w->launches++;
+            io_ok = std::fwrite(host.data(), 1, n16 * 4, f) == n16 * 4;
+        }
+        cudaFree(d_packed);
+    }
+    io_ok = (std::fclose(f) == 0) && io_ok;
+    if (!io_ok) return fail(FS3D_ERR_IO, std::string("short write to ") + path);
+    return FS3D_OK;
+}
+
+int fs3d_load(fs3d_world *w, const char *path) {
+    if (!w || !path) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path);
+    CkptHeader h{};
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "FS3DCKPT", 8) != 0) {
+        std::fclose(f);
+        return fail(FS3D_ERR_IO, std::string(path) + " is not an fs3d checkpoint");
+    }
+    const size_t pb = plane_bytes(w);
+    const uint32_t zb = w->slabs.front().z0, ze = w->slabs.back().z0 + w->slabs.back().nzl;
+    std::string why;
+    if (h.format_version != FS3D_CKPT_VERSION || h.encoding != 1) why = "unknown checkpoint format version / encoding";
+    else if (h.schedule_version != FS3D_SCHEDULE_VERSION) why = "checkpoint was written under another schedule version";
+    else if (h.nx != w->desc.nx || h.ny != w->desc.ny || h.nz != w->desc.nz) why = "checkpoint grid differs from the world's";
+    else if (h.z_begin != zb || h.z_end != ze) why = "checkpoint holds other z-planes than this world";
+    else if (h.payload_bytes != pb / 4 * (uint64_t)(ze - zb)) why = "checkpoint payload size is inconsistent";
+    if (!why.empty()) { std::fclose(f); return fail(FS3D_ERR_INVALID_ARG, why); }
+    int rc = sync_all(w);
+    if (rc) { std::fclose(f); return rc; }
+    // unpack into the BACK buffer, verify the digest there, then flip: a bad file leaves the world untouched
+    const int back = w->cur ^ 1;
+    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / 4));
+    std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / 4));
+    uint64_t sum = 0;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        uint32_t *d_packed = nullptr;
+        const uint32_t cp = std::min(planes_per_chunk, s.nzl);
+        cudaError_t e = cudaMalloc(&d_packed, (size_t)cp * (pb / 4));
+        if (e != cudaSuccess) { std::fclose(f); FS3D_CUDA(e); }
+        for (uint32_t z = 0; z < s.nzl; z += cp) {
+            const uint32_t n = std::min(cp, s.nzl - z);
+            const uint64_t n16 = pb * n / 16;
+            if (std::fread(host.data(), 1, n16 * 4, f) != n16 * 4) {
+                cudaFree(d_packed); std::fclose(f);
+                return fail(FS3D_ERR_IO, std::string(path) + " is truncated");
+            }
+            e = cudaMemcpyAsync(d_packed, host.data(), n16 * 4, cudaMemcpyHostToDevice, s.s_main);
+            if (e == cudaSuccess) {
+                unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(d_packed, n16, owned_ptr(w, s, back) + pb * z);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
+            if (e != cudaSuccess) { cudaFree(d_packed); std::fclose(f); FS3D_CUDA(e); }
+            w->launches++;
+        }
+        cudaFree(d_packed);
+        unsigned long long *d = s.d_scratch + 256, hsum = 0;
+        FS3D_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s.s_main));
+        const uint64_t n16 = pb * s.nzl / 16;
+        digest_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, back), n16, (uint64_t)s.z0 * pb, d);
+        FS3D_CUDA(cudaGetLastError());
+        FS3D_CUDA(cudaMemcpyAsync(&hsum, d, sizeof(hsum), cudaMemcpyDeviceToHost, s.s_main));
+        FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+        sum += hsum;
+    }
+    std::fclose(f);
+    if (sum != h.digest) return fail(FS3D_ERR_IO, std::string(path) + ": digest mismatch (corrupt checkpoint); world unchanged");
+    w->cur = back;
+    w->step = h.step;
+    w->desc.seed = h.seed;
+    return refresh_ghosts(w);   // also marks every activity tile live; ranks of a p2p world call fs3d_slab_push_halos next
 }
 
 }  // extern "C"

@@ -40,6 +40,8 @@ struct RMParams {
     const float *srgb_thr;   // 255 thresholds, or nullptr for linear output
     uint8_t *img;            // W*H*4
     float *depth;            // W*H hit parameter t (inf on miss), may be nullptr
+    unsigned long long *frame;   // non-null: store (float bits of t) << 32 | rgba8 per pixel here instead (this
+                                 // rank's slot of the compositor's frame, possibly peer memory over NVLink)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -205,6 +207,13 @@ __global__ void raymarch_kernel(const RMParams p) {
     }
 
     const size_t pix = (size_t)py * p.W + px;
+    if (p.frame) {
+        // t >= 0, so its bit pattern orders like the float: the compositor takes the 64-bit minimum over ranks
+        const uint32_t rgba = (uint32_t)encode8(r, p.srgb_thr) | ((uint32_t)encode8(g, p.srgb_thr) << 8) |
+                              ((uint32_t)encode8(b, p.srgb_thr) << 16) | 0xFF000000u;
+        p.frame[pix] = ((unsigned long long)__float_as_uint(depth) << 32) | rgba;
+        return;
+    }
     p.img[4 * pix + 0] = encode8(r, p.srgb_thr);
     p.img[4 * pix + 1] = encode8(g, p.srgb_thr);
     p.img[4 * pix + 2] = encode8(b, p.srgb_thr);
@@ -212,9 +221,22 @@ __global__ void raymarch_kernel(const RMParams p) {
     if (p.depth) p.depth[pix] = depth;
 }
 
+// Compositor: per pixel the slot with the smallest hit parameter wins (a miss is +inf and black,
+// exactly what every rank wrote for it, so the minimum is right for misses too).
+__global__ void frame_resolve_kernel(const unsigned long long *frame, uint32_t nslots, size_t npix, uint32_t *rgba) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long best = frame[i];
+        for (uint32_t s = 1; s < nslots; ++s) {
+            const unsigned long long v = frame[(size_t)s * npix + i];
+            best = v < best ? v : best;
+        }
+        rgba[i] = (uint32_t)best;
+    }
+}
+
 // host side, defined in fs3d.cu
 int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode,
-                   uint8_t *host_rgba8, float *host_depth);
+                   uint8_t *host_rgba8, float *host_depth, unsigned long long *frame_slot = nullptr);
 
 // 255 ascending linear-light thresholds: value >= thr[i] encodes to at least i + 1
 inline void srgb_thresholds(float *thr) {

@@ -46,6 +46,8 @@ struct StepParams {
     uint32_t ztile_log2;     // z-tile depth = 1 << ztile_log2 owned planes
     uint32_t nytiles;
     uint32_t step_plus1;     // (uint32)(t + NS)
+    const uint32_t *runs;    // [n][3] = (pair group, it_a, it_b): the live march segments of this launch, built by skip_runs_kernel
+    const uint32_t *nruns;
     // fused halo push over peer memory (PUSH = 1 instantiations only): the warps that compute this
     // slab's first / last owned plane also store it into the z-neighbour's ghost plane (its dst
     // buffer, mapped through CUDA IPC / NVLink) and then add the iterations they finished to the
@@ -143,12 +145,10 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     const uint64_t total = (uint64_t)npg * p.nit;
     // Work split.  Without skipping every iteration costs the same, so the (pair-group x iteration)
     // space is cut into equal contiguous ranges, one per resident warp (no tail, one lead-in each).
-    // With skipping the live work is concentrated in a few y-bands, so SKIP kernels deal chunks of
-    // CHUNK iterations round-robin to the warps instead (a lead-in per chunk, but balanced).
-    constexpr uint32_t CHUNK = 64;
-    const uint32_t cpp = (p.nit + CHUNK - 1) / CHUNK;            // chunks per pair-group
-    const uint64_t nchunks = (uint64_t)npg * cpp;
-    uint64_t chunk = gw;
+    // With skipping only the live segments exist as work: skip_runs_kernel compacts them into a list of
+    // runs (a few y-blocks of one pair group each) that is dealt round-robin to the warps.
+    const uint32_t nruns = SKIP ? *p.nruns : 0xFFFFFFFFu;
+    uint32_t run = gw;
     uint64_t pos = total * gw / nw;
     const uint64_t end = total * (gw + 1) / nw;
 
@@ -158,11 +158,9 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     for (;;) {
         uint32_t pg, it_a, it_b;
         if (SKIP) {
-            if (chunk >= nchunks) break;
-            pg = (uint32_t)(chunk / cpp);
-            it_a = (uint32_t)(chunk - (uint64_t)pg * cpp) * CHUNK;
-            it_b = it_a + CHUNK < p.nit ? it_a + CHUNK : p.nit;
-            chunk += nw;
+            if (run >= nruns) break;
+            pg = p.runs[3u * run]; it_a = p.runs[3u * run + 1u]; it_b = p.runs[3u * run + 2u];
+            run += nw;
         } else {
             if (pos >= end) break;
             pg = (uint32_t)(pos / p.nit);
@@ -177,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
         // the start it would put every bit of inter-GPU skew on the critical path.
         uint32_t pair = p.pair_begin + pg * p.groups + g;
         const bool pair_ok = lane_ok && pair < p.pair_end;
-        if (PUSH && npairs >= 3u && pair_ok) {
+        if (PUSH && !SKIP && npairs >= 3u && pair_ok) {
             const uint32_t pl = pair - p.pair_begin;
             pair = p.pair_begin + (pl < npairs - 2u ? pl + 1u : (pl == npairs - 2u ? 0u : npairs - 1u));
         }
@@ -324,18 +322,6 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
         const uint32_t blk_log2 = SKIP ? p.ytile_log2 - 1u : 31u;
         const uint32_t blk_mask = (1u << blk_log2) - 1u;
         const int32_t ozl = (int32_t)lzl - 1, ozr = (int32_t)lzl;      // owned-plane indices of the two rows
-        auto tile_quiet = [&](int32_t oz, uint32_t yt) -> bool {
-            if (oz < 0 || oz >= (int32_t)p.nzl || yt >= p.nytiles) return true;
-            return p.skip[(size_t)((uint32_t)oz >> p.ztile_log2) * p.nytiles + yt] != 0;
-        };
-        auto block_skippable = [&](uint32_t bi) -> bool {
-            bool q = true;
-            if (pair_ok) {
-                q = tile_quiet(ozl, bi) && tile_quiet(ozr, bi);
-                if (bi > 0) q = q && tile_quiet(ozl, bi - 1) && tile_quiet(ozr, bi - 1);
-            }
-            return __all_sync(ONES, q);
-        };
         auto mark = [&](int32_t oz, uint32_t yt) {
             if (oz >= 0 && oz < (int32_t)p.nzl && yt < p.nytiles)
                 p.last_active[(size_t)((uint32_t)oz >> p.ztile_log2) * p.nytiles + yt] = p.step_plus1;
@@ -347,21 +333,13 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
             en_main = 0; en_strad = 0;
         };
 
-        // `it` runs over [it_a, it_b); after a jump (segment start or skipped block) the LEAD
-        // iterations below `it` are replayed without storing (`warm` counts them down)
+        // `it` runs over [it_a, it_b); the LEAD iterations below it_a are replayed first without storing
+        // (`warm` counts them down).  SKIP runs start and end on y-block boundaries and hold live blocks only.
         bool loaded = false;
-        bool next_skip = SKIP ? block_skippable(it_a >> blk_log2) : false;
         uint32_t it = it_a;
         uint32_t warm = 0;             // > 0: this iteration only rebuilds carried planes
         bool need_restart = true;
         while (it < it_b) {
-            if (SKIP && next_skip && warm == 0) {   // jump over a provably static block; nothing is read or written
-                const uint32_t nb = ((it >> blk_log2) + 1u) << blk_log2;
-                it = nb < it_b ? nb : it_b;
-                need_restart = true; loaded = false;
-                if (it < it_b) next_skip = block_skippable(it >> blk_log2);
-                continue;
-            }
             if (need_restart) {
                 reset_carry();                      // STONE below the floor; harmless garbage otherwise
                 warm = it < LEAD ? it : LEAD;
@@ -381,11 +359,9 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                     if (!(wok[j] && y1 + 1u < p.ny)) hi[j][r] = {ONES, ONES};
                 }
 
-            // decide about the next iteration now, so that its loads are in flight while we evaluate
+            // the next iteration's loads are in flight while this one is evaluated
             const uint32_t nxt = it + 1;
-            const bool boundary = SKIP && warm == 0 && (nxt & blk_mask) == 0u;
-            if (boundary && nxt < it_b) next_skip = block_skippable(nxt >> blk_log2);
-            loaded = nxt < it_b && !(boundary && next_skip);
+            loaded = nxt < it_b;
             if (loaded) load_pair(nxt);
 
             uint32_t e1, e2, e3 = 0, e4 = 0;
@@ -481,6 +457,73 @@ __global__ void skip_map_kernel(const uint32_t *last_active, uint8_t *skip, uint
     for (int o = 16; o > 0; o >>= 1) run += __shfl_xor_sync(0xFFFFFFFFu, run, o);
     if ((threadIdx.x & 31) == 0 && run) atomicAdd(&stats[0], (unsigned long long)run);
     if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] = n;
+}
+
+// The live march segments of one launch, for the SKIP kernels: one WARP per pair group tests its
+// y-blocks 32 at a time (a block is static iff the tiles of both rows at y-tile b and b − 1 are quiet —
+// the test the march used to make per block), and lane 0 emits every maximal run of live blocks,
+// chopped into pieces of `chop` blocks so that every marching warp gets several runs.  Order in the
+// list is arbitrary: blocks write disjoint planes.
+__global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t ztile_log2, uint32_t blk_log2,
+                                 uint32_t nzl, uint32_t lz_first, uint32_t pair_begin, uint32_t pair_end,
+                                 uint32_t groups, uint32_t nit, uint32_t nw, const unsigned long long *stats,
+                                 uint32_t *runs, uint32_t *nruns) {
+    const uint32_t npairs = pair_end - pair_begin;
+    const uint32_t npg = (npairs + groups - 1) / groups;
+    const uint32_t blk = 1u << blk_log2;
+    const uint32_t nblk = (nit + blk - 1u) >> blk_log2;
+    const uint32_t lane = threadIdx.x & 31u;
+    // chop length from the live tile fraction of this step: aim at >= 4 runs per warp, at most 64 iterations
+    const unsigned long long live = stats[0], tot = stats[1];
+    const unsigned long long est = tot ? (unsigned long long)npg * nit * live / tot : (unsigned long long)npg * nit;
+    const unsigned long long per = est / (nw ? nw : 1u);
+    const uint32_t chop = per >= 16ull * blk ? 4u : (per >= 8ull * blk ? 2u : 1u);
+    auto quiet = [&](int32_t oz, uint32_t yt) -> bool {
+        if (oz < 0 || oz >= (int32_t)nzl || yt >= nytiles) return true;
+        return skip[(size_t)((uint32_t)oz >> ztile_log2) * nytiles + yt] != 0;
+    };
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t pg = blockIdx.x * wpb + (threadIdx.x >> 5); pg < npg; pg += gridDim.x * wpb) {
+        // two sweeps over the blocks: count this pair group's runs, reserve them with ONE atomic, then write
+        // them in y order (so neighbouring warps of the march get neighbouring segments of one pair)
+        uint32_t count = 0, at = 0;
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            int32_t start = -1;
+            for (uint32_t base = 0; base <= nblk; base += 32u) {
+                const uint32_t bi = base + lane;
+                bool act = false;
+                if (bi < nblk) {
+                    for (uint32_t g = 0; g < groups && !act; ++g) {
+                        const uint32_t pair = pair_begin + pg * groups + g;
+                        if (pair >= pair_end) break;
+                        const int32_t ozl = (int32_t)(lz_first + 2u * pair) - 1, ozr = ozl + 1;
+                        bool q = quiet(ozl, bi) && quiet(ozr, bi);
+                        if (bi > 0) q = q && quiet(ozl, bi - 1) && quiet(ozr, bi - 1);
+                        act = !q;
+                    }
+                }
+                const uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
+                if (lane == 0) {
+                    for (uint32_t k = 0; k < 32u && base + k <= nblk; ++k) {
+                        const uint32_t b = base + k;
+                        const bool a = (mask >> k) & 1u;
+                        if (start >= 0 && (!a || b - (uint32_t)start == chop)) {
+                            if (sweep == 0) {
+                                ++count;
+                            } else {
+                                const uint32_t e = b << blk_log2;
+                                runs[3u * at] = pg; runs[3u * at + 1u] = (uint32_t)start << blk_log2; runs[3u * at + 2u] = e < nit ? e : nit;
+                                ++at;
+                            }
+                            start = -1;
+                        }
+                        if (a && start < 0) start = (int32_t)b;
+                    }
+                }
+            }
+            if (sweep == 0 && lane == 0 && count) at = atomicAdd(nruns, count);
+        }
+    }
 }
 
 }  // namespace fs3d

@@ -247,9 +247,11 @@ class SlabWorld:
     def raymarch(self, **cam):
         """Every rank marches its own slab (fs3d_raymarch_depth); rank 0 keeps, per pixel, the colour of
         the nearest hit.  Returns the (H, W, 4) uint8 image on rank 0, else None."""
-        img, depth = self.engine.world.raymarch(with_depth=True, **cam)
         if self.world_size == 1:
-            return img
+            return self.engine.world.raymarch(**cam)
+        if self.p2p:
+            return self._raymarch_fused(**cam)
+        img, depth = self.engine.world.raymarch(with_depth=True, **cam)
         dev = self.engine.reduce_device()
         timg = torch.from_numpy(img).to(dev)
         tdep = torch.from_numpy(depth).to(dev)
@@ -264,6 +266,21 @@ class SlabWorld:
         allimg = torch.stack(imgs)                  # (ranks, H, W, 4)
         out = torch.gather(allimg, 0, best[None, :, :, None].expand(1, *allimg.shape[1:]))[0]
         return out.cpu().numpy()
+
+    def _raymarch_fused(self, width=850, height=450, **cam):
+        """March + composite over peer memory: every rank's kernel stores (t, rgba) into its slot of rank
+        0's frame over NVLink; rank 0 takes the per-pixel minimum.  No host copy, no collective."""
+        w = self.engine.world
+        if getattr(self, "_frame_dims", None) != (width, height):
+            blob = [w.frame_export(width, height, self.world_size) if self.rank == 0 else None]
+            dist.broadcast_object_list(blob, src=0, group=self.group)
+            w.frame_attach(blob[0], self.rank)
+            self._frame_dims = (width, height)
+        dist.barrier(group=self.group)          # rank 0 has resolved the previous frame: slots may be overwritten
+        w.raymarch_to_frame(**cam)
+        w.sync()
+        dist.barrier(group=self.group)          # every slot is complete
+        return w.frame_resolve(width, height) if self.rank == 0 else None
 
     def close(self):
         self.engine.close()

@@ -20,7 +20,7 @@ FLAG_NO_FUSE = 2
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
-               -6: "OOM", -7: "UNSUPPORTED"}
+               -6: "OOM", -7: "UNSUPPORTED", -8: "IO"}
 
 
 class Fs3dError(RuntimeError):
@@ -44,6 +44,8 @@ class VoxelWorld:
     VoxelWorld(..., slab=(z_begin, z_end)) owns one rank's slab on the current CUDA device; the
     caller drives the halo exchange (see slab.SlabWorld).
     """
+
+    IPC_BLOB_BYTES = 256
 
     def __init__(self, nx, ny, nz, seed=1, n_gpus=1, devices=None, flags=0, slab=None):
         self._lib = _lib.load()
@@ -145,6 +147,15 @@ class VoxelWorld:
                                         grid_out.ctypes.data_as(C.c_void_p), int(n)))
         return grid_out
 
+    # ---- checkpoint (format in include/fs3d.h; numpy reader/writer in checkpoint.py) ----
+    def save(self, path):
+        _check(self._lib.fs3d_save(self._h, str(path).encode()))
+
+    def load(self, path):
+        _check(self._lib.fs3d_load(self._h, str(path).encode()))
+        from . import checkpoint
+        self.seed = int(checkpoint.read_header(path)["seed"])   # the world now runs on the checkpoint's seed
+
     # ---- reductions ----
     def histogram(self):
         h = (C.c_uint64 * 256)()
@@ -192,13 +203,29 @@ class VoxelWorld:
         _check(self._lib.fs3d_raymarch(self._h, C.byref(cam), width, height, mode, img.ctypes.data_as(C.c_void_p)))
         return img
 
+    # ---- fused multi-rank ray-march (see slab.SlabWorld.raymarch) ----
+    def frame_export(self, width, height, n_slots):
+        buf = C.create_string_buffer(self.IPC_BLOB_BYTES)
+        _check(self._lib.fs3d_frame_export(self._h, int(width), int(height), int(n_slots), buf, self.IPC_BLOB_BYTES))
+        return buf.raw
+
+    def frame_attach(self, blob, slot):
+        _check(self._lib.fs3d_frame_attach(self._h, C.create_string_buffer(blob, self.IPC_BLOB_BYTES), int(slot)))
+
+    def raymarch_to_frame(self, pos=(0.0, 0.0, -5.0), yaw_deg=0.0, aspect=1700.0 / 900.0, mode=RM_VOXELS):
+        cam = _lib.Camera((C.c_float * 3)(*pos), yaw_deg, aspect)
+        _check(self._lib.fs3d_raymarch_to_frame(self._h, C.byref(cam), mode))
+
+    def frame_resolve(self, width, height, out=None):
+        img = np.empty((height, width, 4), dtype=np.uint8) if out is None else out
+        _check(self._lib.fs3d_frame_resolve(self._h, img.ctypes.data_as(C.c_void_p)))
+        return img
+
     # ---- one-process-per-GPU slab protocol (see slab.SlabWorld) ----
     def slab_halo(self, back):
         h = _lib.Halo()
         _check(self._lib.fs3d_slab_halo(self._h, int(back), C.byref(h)))
         return h
-
-    IPC_BLOB_BYTES = 256
 
     def slab_ipc_export(self):
         buf = C.create_string_buffer(self.IPC_BLOB_BYTES)

@@ -54,6 +54,7 @@ extern "C" {
 #define FS3D_ERR_CUDA          -5
 #define FS3D_ERR_OOM           -6
 #define FS3D_ERR_UNSUPPORTED   -7
+#define FS3D_ERR_IO            -8
 
 /* fs3d_desc.flags */
 #define FS3D_FLAG_SKIP_SETTLED  1u   /* settled-tile skipping (bit-exact; SCHEDULE.md §4) */
@@ -181,6 +182,36 @@ int  fs3d_slab_step_finish(fs3d_world *w);
 int  fs3d_slab_ipc_export(fs3d_world *w, void *blob, uint64_t blob_bytes);
 int  fs3d_slab_ipc_attach(fs3d_world *w, const void *lower_blob, const void *upper_blob);
 int  fs3d_slab_push_halos(fs3d_world *w);
+
+/* ---- fused multi-rank ray-march (one process per GPU): march + composite over peer memory ----
+ * The compositor rank allocates a frame of n_slots x (width x height) 64-bit words and exports it;
+ * every rank (the compositor too) attaches with its own slot.  fs3d_raymarch_to_frame marches this
+ * rank's slab and its kernel stores (hit parameter bits << 32 | rgba8) for every pixel straight into
+ * that slot — NVLink peer stores for the other ranks, no host copy, no collective.  After every rank
+ * has synchronised (fs3d_sync + a barrier of the caller's choice) the compositor calls
+ * fs3d_frame_resolve: per pixel the slot with the smallest hit parameter wins (same image as one
+ * world marching all slabs), copied to host_rgba8.  Barrier again before the next frame is marched.
+ * Camera and shading are those of shaders/fs_raymarch.{vert,frag} as for fs3d_raymarch. */
+int  fs3d_frame_export(fs3d_world *w, uint32_t width, uint32_t height, uint32_t n_slots, void *blob, uint64_t blob_bytes);
+int  fs3d_frame_attach(fs3d_world *w, const void *blob, uint32_t slot);
+int  fs3d_raymarch_to_frame(fs3d_world *w, const fs3d_camera *cam, uint32_t mode);   /* asynchronous */
+int  fs3d_frame_resolve(fs3d_world *w, uint8_t *host_rgba8);
+
+/* ---- checkpoint (the reference has no on-disk state, src/engine holds none) ----
+ * One file per world handle (per rank for slab worlds).  Little-endian:
+ *   offset  0  char[8]  "FS3DCKPT"
+ *           8  u32 format version (FS3D_CKPT_VERSION)   12  u32 schedule version
+ *          16  u32 nx, ny, nz                            28  u32 z_begin, z_end (planes in the file)
+ *          36  u32 encoding (1)                          40  u64 step index   48  u64 seed
+ *          56  u64 digest of these planes                64  u64 payload bytes   72  u64 reserved (0)
+ *   offset 80  payload: cells in x-fastest order, 2 bits each, cell i in bits 2(i & 3) of byte i >> 2
+ * fs3d_load restores cells, step index and seed (so the run continues bit-identically), verifies
+ * dimensions, plane range, schedule version and the digest, and leaves the world untouched on any
+ * error.  Ranks of a fused-halo-push world call fs3d_slab_push_halos + barrier afterwards. */
+#define FS3D_CKPT_VERSION       1
+#define FS3D_CKPT_HEADER_BYTES  80
+int  fs3d_save(fs3d_world *w, const char *path);
+int  fs3d_load(fs3d_world *w, const char *path);
 
 const char *fs3d_last_error(void);
 int  fs3d_schedule_version(void);

@@ -52,6 +52,13 @@ def main():
                 if ref.digest() != d:
                     ok = False
                     print(f"MISMATCH {nx}x{ny}x{nz} p2p after 50 async steps", flush=True)
+        # every rank marches its slab; rank 0 composites (p2p: in the kernels over peer memory, else NCCL gather)
+        cam = dict(pos=(0.2, -0.3, -1.3), yaw_deg=20.0, aspect=16.0 / 9.0, width=192, height=108, mode=fs3d.RM_VOXELS)
+        for _ in range(2):
+            img = sw.raymarch(**cam)
+            if rank == 0 and not np.array_equal(img, ref.raymarch(**cam)):
+                ok = False
+                print(f"MISMATCH {nx}x{ny}x{nz} p2p={p2p} raymarch composite", flush=True)
         h = sw.histogram()
         if rank == 0:
             ok = ok and np.array_equal(h, ref.histogram())

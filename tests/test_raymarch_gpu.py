@@ -73,3 +73,25 @@ def test_palette_and_multislab_raymarch(fs3d, oracle):
         img[closer] = im[closer]
         best = np.where(closer, d, best)
     assert np.array_equal(img, ref)
+
+
+def test_frame_path_single_rank_equals_raymarch(fs3d, oracle):
+    # fs3d_frame_export / attach / raymarch_to_frame / resolve with one slot == fs3d_raymarch
+    # (the multi-rank composite over peer memory is exercised by tests/run_slab_ranks.py)
+    nx, ny, nz = 64, 48, 40
+    g = oracle.generate(nx, ny, nz, 4, 3)
+    cam = dict(pos=(0.3, -0.2, -1.4), yaw_deg=12.0, aspect=16.0 / 9.0)
+    with fs3d.VoxelWorld(nx, ny, nz, slab=(0, nz)) as w:
+        w.upload(g)
+        with pytest.raises(fs3d.Fs3dError):
+            w.raymarch_to_frame(**cam)                 # no frame yet
+        blob = w.frame_export(160, 90, 1)
+        w.frame_attach(blob, 0)
+        with pytest.raises(fs3d.Fs3dError):
+            w.frame_attach(blob, 1)                    # slot outside the frame
+        for mode in (fs3d.RM_VOXELS, fs3d.RM_VOXELS | fs3d.RM_SRGB, fs3d.RM_SDF_SPHERE):
+            w.raymarch_to_frame(mode=mode, **cam)
+            w.sync()
+            img = w.frame_resolve(160, 90)
+            assert np.array_equal(img, w.raymarch(mode=mode, width=160, height=90, **cam))
+            assert np.array_equal(img, oracle.raymarch(g if mode != fs3d.RM_SDF_SPHERE else None, mode=mode, width=160, height=90, **cam))
