@@ -473,36 +473,51 @@ __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t
     const uint32_t blk = 1u << blk_log2;
     const uint32_t nblk = (nit + blk - 1u) >> blk_log2;
     const uint32_t lane = threadIdx.x & 31u;
-    // chop length from the live tile fraction of this step: aim at >= 4 runs per warp, at most 64 iterations
+    // Chop length (1, 2 or 4 blocks) from the live tile fraction of this step: every run re-reads LEAD plane
+    // pairs, so long runs waste least, but the warps must also get equal shares; take the length with
+    // the smallest estimated makespan  ceil(runs / warps) x (iterations per run + lead-in).
     const unsigned long long live = stats[0], tot = stats[1];
-    const unsigned long long est = tot ? (unsigned long long)npg * nit * live / tot : (unsigned long long)npg * nit;
-    const unsigned long long per = est / (nw ? nw : 1u);
-    const uint32_t chop = per >= 16ull * blk ? 4u : (per >= 8ull * blk ? 2u : 1u);
+    const unsigned long long blocks_live = tot ? ((unsigned long long)npg * nblk * live + tot - 1) / tot : (unsigned long long)npg * nblk;
+    uint32_t chop = 4u;
+    unsigned long long best = ~0ull;
+    for (uint32_t c = 4u; c >= 1u; c >>= 1) {
+        const unsigned long long nr = (blocks_live + c - 1) / c;
+        const unsigned long long span = ((nr + nw - 1) / (nw ? nw : 1u)) * (unsigned long long)(c * blk + 3u);
+        if (span < best) { best = span; chop = c; }
+    }
     auto quiet = [&](int32_t oz, uint32_t yt) -> bool {
         if (oz < 0 || oz >= (int32_t)nzl || yt >= nytiles) return true;
         return skip[(size_t)((uint32_t)oz >> ztile_log2) * nytiles + yt] != 0;
     };
     const uint32_t wpb = blockDim.x >> 5;
     for (uint32_t pg = blockIdx.x * wpb + (threadIdx.x >> 5); pg < npg; pg += gridDim.x * wpb) {
+        // live mask of blocks [base, base + 32): the four tile flags of a block are loaded side by side
+        auto live_mask = [&](uint32_t base) -> uint32_t {
+            const uint32_t bi = base + lane;
+            bool act = false;
+            if (bi < nblk) {
+                for (uint32_t g = 0; g < groups; ++g) {
+                    const uint32_t pair = pair_begin + pg * groups + g;
+                    if (pair >= pair_end) break;
+                    const int32_t ozl = (int32_t)(lz_first + 2u * pair) - 1, ozr = ozl + 1;
+                    const bool q0 = quiet(ozl, bi), q1 = quiet(ozr, bi);
+                    const bool q2 = bi == 0u || quiet(ozl, bi - 1), q3 = bi == 0u || quiet(ozr, bi - 1);
+                    act = act || !(q0 & q1 & q2 & q3);
+                }
+            }
+            return __ballot_sync(0xFFFFFFFFu, act);
+        };
         // two sweeps over the blocks: count this pair group's runs, reserve them with ONE atomic, then write
         // them in y order (so neighbouring warps of the march get neighbouring segments of one pair)
+        constexpr uint32_t CACHE = 4;              // masks of the first sweep are kept for up to 128 blocks
+        uint32_t cache[CACHE];
         uint32_t count = 0, at = 0;
         for (int sweep = 0; sweep < 2; ++sweep) {
             int32_t start = -1;
-            for (uint32_t base = 0; base <= nblk; base += 32u) {
-                const uint32_t bi = base + lane;
-                bool act = false;
-                if (bi < nblk) {
-                    for (uint32_t g = 0; g < groups && !act; ++g) {
-                        const uint32_t pair = pair_begin + pg * groups + g;
-                        if (pair >= pair_end) break;
-                        const int32_t ozl = (int32_t)(lz_first + 2u * pair) - 1, ozr = ozl + 1;
-                        bool q = quiet(ozl, bi) && quiet(ozr, bi);
-                        if (bi > 0) q = q && quiet(ozl, bi - 1) && quiet(ozr, bi - 1);
-                        act = !q;
-                    }
-                }
-                const uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
+            for (uint32_t base = 0, wi = 0; base <= nblk; base += 32u, ++wi) {
+                uint32_t mask;
+                if (sweep == 0) { mask = live_mask(base); if (wi < CACHE) cache[wi] = mask; }
+                else mask = wi < CACHE ? cache[wi] : live_mask(base);
                 if (lane == 0) {
                     for (uint32_t k = 0; k < 32u && base + k <= nblk; ++k) {
                         const uint32_t b = base + k;

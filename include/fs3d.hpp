@@ -54,6 +54,10 @@ public:
     void waitForSimulation() { check(fs3d_sync(mWorld)); }          // cf. Renderer::waitForGraphics
     uint64_t stepIndex() { uint64_t s = 0; check(fs3d_step_index(mWorld, &s)); return s; }
 
+    // checkpoint: cells + step index + seed (format in fs3d.h); load() continues the run bit-identically
+    void save(const std::string &path) { check(fs3d_save(mWorld, path.c_str())); }
+    void load(const std::string &path) { check(fs3d_load(mWorld, path.c_str())); }
+
     std::array<uint64_t, 256> histogram() { std::array<uint64_t, 256> h{}; check(fs3d_histogram(mWorld, h.data())); return h; }
     uint64_t digest() { uint64_t d = 0; check(fs3d_digest(mWorld, &d)); return d; }
 

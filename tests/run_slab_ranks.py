@@ -20,10 +20,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    cases = [(64, 24, 18, 3, 12, True), (64, 24, 18, 3, 12, False), (2048, 32, 24, 4, 10, True),
-             (2048, 32, 24, 4, 10, False), (256, 256, 256, 2, 40, True), (4096, 16, 20, 3, 6, True)]
-    for (nx, ny, nz, scene, steps, p2p) in cases:
-        sw = SlabWorld(nx, ny, nz, seed=5, p2p=p2p)
+    SK = fs3d.FLAG_SKIP_SETTLED
+    cases = [(64, 24, 18, 3, 12, True, 0), (64, 24, 18, 3, 12, False, 0), (2048, 32, 24, 4, 10, True, 0),
+             (2048, 32, 24, 4, 10, False, 0), (256, 256, 256, 2, 40, True, 0), (4096, 16, 20, 3, 6, True, 0),
+             (64, 96, 48, 1, 60, True, SK), (64, 96, 48, 1, 30, False, SK), (4096, 70, 16, 4, 12, True, SK)]
+    for (nx, ny, nz, scene, steps, p2p, flags) in cases:
+        sw = SlabWorld(nx, ny, nz, seed=5, p2p=p2p, flags=flags)
         assert sw.p2p == p2p
         sw.generate(scene, 3)
         ref = None

@@ -70,3 +70,34 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), os.path.join(dirpath, f)
+
+
+def _build_engine_loop(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "engine_loop")
+    lib_dir = os.path.join(ROOT, "fallingsand3d_b200")
+    cmd = ["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "engine_loop.cpp"), "-L" + lib_dir, "-lfs3d", "-Wl,-rpath," + lib_dir, "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+@pytest.mark.skipif(_has_cuda(), reason="only meaningful on a box without a GPU")
+def test_cpp_wrapper_builds_and_reports_errors_like_the_engine(fs3d, tmp_path):
+    # include/fs3d.hpp + examples/engine_loop.cpp compile as plain C++17 against the C ABI; without a GPU
+    # the wrapper logs "ERROR: ..." and throws (util::displayError, debug.cpp:23-27) -> the example exits 2
+    import subprocess
+    exe = _build_engine_loop(tmp_path)
+    res = subprocess.run([exe, "32", "2"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert res.returncode == 2 and res.stderr.startswith("ERROR: fs3d:")
+
+
+@pytest.mark.gpu
+def test_cpp_engine_loop_runs_on_the_gpu(fs3d, tmp_path):
+    import subprocess
+    exe = _build_engine_loop(tmp_path)
+    res = subprocess.run([exe, "64", "100"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "steps 100" in res.stdout and "sand 4096 -> 4096" in res.stdout
+    assert os.path.getsize(tmp_path / "frame_100.ppm") == len("P6\n850 450\n255\n") + 850 * 450 * 3

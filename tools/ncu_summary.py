@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Condenses `ncu --page raw --csv` dumps of the step kernels into the few metrics DESIGN.md quotes and
+refreshes profiles/traffic.json (read by bench.py for roofline.traffic).
+
+  python tools/ncu_summary.py TAG      (reads profiles/TAG_step_kernel_*_ncu_full_raw.csv)
+"""
+import csv
+import glob
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_static",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+
+
+def main():
+    tag = sys.argv[1]
+    lines, traffic = [], {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"{tag}_step_kernel_*_ncu_full_raw.csv"))):
+        name = os.path.basename(path)[len(tag) + len("_step_kernel_"):-len("_ncu_full_raw.csv")]
+        rows = list(csv.reader(open(path)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        col = {h: i for i, h in enumerate(hdr)}
+        tot = []
+        for d in data:
+            lines.append(f"--- {name}: {d[col['Kernel Name']]}")
+            for m in WANT:
+                if m in col:
+                    lines.append(f"{m:70s} {d[col[m]]:>18s} {units[col[m]]}")
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            tot.append(sum(float(d[col[m]]) * scale[units[col[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
+        traffic[name] = sum(tot) / len(tot)
+    with open(os.path.join(ROOT, "profiles", f"{tag}_step_kernel_ncu_summary.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    out = {"2048": traffic.get("single_2048"), "2048_fused": traffic.get("fused_2048"),
+           "4096x4096x512": traffic.get("single_4096w"), "4096x4096x512_fused": traffic.get("fused_4096w"),
+           "source": f"profiles/{tag}_step_kernel_*_ncu_full_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                     "(mean over the captured launches: both x-offsets, and both step parities for the single-step "
+                     "kernels). 2048 = 2048^3 grid, 17.18 GB algorithmic per single-step launch; a fused launch "
+                     "advances two steps (34.36 GB algorithmic by the 2 B/update definition) on the same traffic. "
+                     "4096x4096x512 = one rank's slab of 4096^3 on 8 GPUs (warp-pair kernels), same voxel count"}
+    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("\n".join(lines[:12]))
+    print(json.dumps(out)[:300])
+
+
+if __name__ == "__main__":
+    main()
