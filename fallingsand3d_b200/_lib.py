@@ -41,6 +41,7 @@ SIGNATURES = {
     "fs3d_set_cell": (C.c_int, [_W, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]),
     "fs3d_get_cell": (C.c_int, [_W, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
     "fs3d_fill_box": (C.c_int, [_W, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint8]),
+    "fs3d_paint_sphere": (C.c_int, [_W, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_uint8, C.c_int]),
     "fs3d_generate": (C.c_int, [_W, C.c_int, C.c_uint64]),
     "fs3d_upload": (C.c_int, [_W, C.c_void_p]),
     "fs3d_download": (C.c_int, [_W, C.c_void_p]),

@@ -183,4 +183,23 @@ __global__ void fill_box_kernel(uint8_t *owned, uint32_t nx, uint32_t ny, uint32
     }
 }
 
+// brush for the engine's paint/erase input: every cell of this slab whose centre lies within `radius` cells of
+// (cx, cy, cz) becomes m; with only_empty, cells that already hold a material are left alone
+__global__ void paint_sphere_kernel(uint8_t *owned, uint32_t nx, uint32_t ny, uint32_t nzg, uint32_t z0, uint32_t nzl,
+                                    int64_t cx, int64_t cy, int64_t cz, int64_t radius, uint8_t m, int only_empty) {
+    const int64_t x0 = cx - radius < 0 ? 0 : cx - radius, x1 = cx + radius >= nx ? (int64_t)nx - 1 : cx + radius;
+    const int64_t y0 = cy - radius < 0 ? 0 : cy - radius, y1 = cy + radius >= ny ? (int64_t)ny - 1 : cy + radius;
+    const int64_t zb0 = cz - radius < 0 ? 0 : cz - radius, zb1 = cz + radius >= nzg ? (int64_t)nzg - 1 : cz + radius;
+    if (x1 < x0 || y1 < y0 || zb1 < zb0) return;
+    const uint64_t bx = x1 - x0 + 1, by = y1 - y0 + 1, bz = zb1 - zb0 + 1, n = bx * by * bz;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int64_t x = x0 + (int64_t)(i % bx), y = y0 + (int64_t)((i / bx) % by), z = zb0 + (int64_t)(i / (bx * by));
+        const int64_t dx = x - cx, dy = y - cy, dz = z - cz;
+        if (dx * dx + dy * dy + dz * dz > radius * radius) continue;
+        if (z < (int64_t)z0 || z >= (int64_t)z0 + nzl) continue;
+        uint8_t *c = owned + x + (uint64_t)nx * (y + (uint64_t)ny * (z - z0));
+        if (!only_empty || *c == FS3D_EMPTY) *c = m;
+    }
+}
+
 }  // namespace fs3d

@@ -101,6 +101,11 @@ class VoxelWorld:
         b = (C.c_uint32 * 3)(*hi)
         _check(self._lib.fs3d_fill_box(self._h, a, b, m))
 
+    def paint_sphere(self, centre, radius, m, only_empty=False):
+        """Brush: cells within `radius` of `centre` (x, y, z; may lie outside the grid) become m."""
+        _check(self._lib.fs3d_paint_sphere(self._h, int(centre[0]), int(centre[1]), int(centre[2]), int(radius), int(m),
+                                           1 if only_empty else 0))
+
     def generate(self, scene_id, seed=None):
         _check(self._lib.fs3d_generate(self._h, int(scene_id), self.seed if seed is None else int(seed)))
 

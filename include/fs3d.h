@@ -120,6 +120,10 @@ void fs3d_destroy(fs3d_world *w);
 int  fs3d_set_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t m);
 int  fs3d_get_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t *m);
 int  fs3d_fill_box(fs3d_world *w, const uint32_t lo[3], const uint32_t hi[3], uint8_t m); /* half-open */
+/* Brush for paint / erase input (the engine's key and mouse events, src/engine/window.cpp:34-107): every cell
+ * whose centre lies within `radius` cells of (cx, cy, cz) becomes m (FS3D_EMPTY erases); the centre may lie
+ * outside the grid; with only_empty != 0 cells that already hold a material are kept. */
+int  fs3d_paint_sphere(fs3d_world *w, int32_t cx, int32_t cy, int32_t cz, uint32_t radius, uint8_t m, int only_empty);
 int  fs3d_generate(fs3d_world *w, int scene_id, uint64_t seed);
 int  fs3d_upload(fs3d_world *w, const uint8_t *host);    /* host: the planes this world holds, x fastest */
 int  fs3d_download(fs3d_world *w, uint8_t *host);

@@ -43,6 +43,9 @@ public:
     void setCell(uint32_t x, uint32_t y, uint32_t z, uint8_t m) { check(fs3d_set_cell(mWorld, x, y, z, m)); }
     uint8_t getCell(uint32_t x, uint32_t y, uint32_t z) { uint8_t m = 0; check(fs3d_get_cell(mWorld, x, y, z, &m)); return m; }
     void fillBox(std::array<uint32_t, 3> lo, std::array<uint32_t, 3> hi, uint8_t m) { check(fs3d_fill_box(mWorld, lo.data(), hi.data(), m)); }
+    void paintSphere(int32_t cx, int32_t cy, int32_t cz, uint32_t radius, uint8_t m, bool onlyEmpty = false) {
+        check(fs3d_paint_sphere(mWorld, cx, cy, cz, radius, m, onlyEmpty ? 1 : 0));
+    }
     void generate(int sceneId, uint64_t seed) { check(fs3d_generate(mWorld, sceneId, seed)); }
     void upload(const std::vector<uint8_t> &grid) {
         if (grid.size() != (size_t)mNx * mNy * mNz) displayError("VoxelWorld::upload: wrong grid size");

@@ -204,3 +204,50 @@ def test_step_host_streams_a_host_grid(fs3d, oracle, dims):
         with pytest.raises(fs3d.Fs3dError) as ei:
             w.step_host(bad, out, 1)
         assert ei.value.code == -3
+
+
+def test_paint_sphere_brush(fs3d, oracle):
+    import torch
+    k = torch.cuda.device_count()
+    nx, ny, nz = 64, 40, 30
+    zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    for devices in (None, [i % k for i in range(3)]):
+        g = oracle.generate(nx, ny, nz, 2, 1)
+        with fs3d.VoxelWorld(nx, ny, nz, seed=3, devices=devices) as w:
+            w.upload(g)
+            for (c, r, m, only_empty) in [((20, 30, 12), 6, S, False), ((-3, 20, 29), 9, W, True), ((40, 5, 10), 4, E, False),
+                                          ((63, 39, 0), 0, X, False), ((200, 200, 200), 5, S, False)]:
+                w.paint_sphere(c, r, m, only_empty)
+                mask = (xx - c[0]) ** 2 + (yy - c[1]) ** 2 + (zz - c[2]) ** 2 <= r * r
+                if only_empty:
+                    mask &= g == E
+                g[mask] = m
+                assert np.array_equal(w.download(), g), (c, r, m)
+            w.step(12)                      # a painted world steps like an uploaded one (ghost planes were refreshed)
+            oracle.run(g, 3, 0, 12)
+            assert np.array_equal(w.download(), g)
+            with pytest.raises(fs3d.Fs3dError) as ei:
+                w.paint_sphere((1, 1, 1), 2, 9)
+            assert ei.value.code == -3
+
+
+def test_full_size_properties_2048(fs3d):
+    # BASELINE's headline size: conservation, fused == unfused, skipping == not skipping, determinism
+    n = 2048
+    digs = {}
+    for name, flags in (("fused", 0), ("unfused", fs3d.FLAG_NO_FUSE), ("skip", fs3d.FLAG_SKIP_SETTLED)):
+        with fs3d.VoxelWorld(n, n, n, seed=1, flags=flags) as w:
+            w.generate(fs3d.SCENE_MIXED_NOISE, 1)
+            h0 = w.histogram()
+            assert int(h0.sum()) == n ** 3
+            w.step(13)                     # odd: pair passes plus a single pass
+            assert np.array_equal(w.histogram(), h0)
+            digs[name] = w.digest()
+    assert digs["fused"] == digs["unfused"] == digs["skip"]
+
+
+@pytest.mark.parametrize("dims,steps", [((2048, 2048, 4), 6), ((4096, 1024, 4), 6), ((1024, 1024, 8), 8)])
+def test_full_extent_planes_match_oracle(fs3d, oracle, dims, steps):
+    # full BASELINE x and y extents (every word position of a row, every march segment shape), few planes in z
+    nx, ny, nz = dims
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=4, seed=2, steps=steps, every=steps)
