@@ -55,6 +55,7 @@ struct Slab {
         unsigned long long *flags = nullptr;   // neighbour's d_flags
         uint32_t nzl = 0;
         bool valid = false;
+        bool ipc = false;                      // mapped through CUDA IPC (another process) rather than plain peer access
     } peer_lo, peer_hi;
     // fused multi-rank ray-march: the compositor's frame (one slot of W x H 64-bit words per rank)
     struct Frame {
@@ -184,7 +185,7 @@ static void free_slab(Slab &s) {
     if (s.s_comm) cudaStreamSynchronize(s.s_comm);
     for (int b = 0; b < 2; ++b) if (s.buf[b]) cudaFree(s.buf[b]);
     for (Slab::Peer *pr : {&s.peer_lo, &s.peer_hi}) {
-        if (!pr->valid) continue;
+        if (!pr->valid || !pr->ipc) continue;
         for (int b = 0; b < 2; ++b) if (pr->buf[b]) cudaIpcCloseMemHandle(pr->buf[b]);
         if (pr->flags) cudaIpcCloseMemHandle(pr->flags);
     }
@@ -368,6 +369,17 @@ static int step_pass(fs3d_world *w, int ns) {
         if (rc) return rc;
         // every warp of an edge pair adds the iterations it finished: nit of this pass x warps per pair
         if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
+    } else if (w->p2p) {
+        // one process, one slab per GPU, peer access both ways: the same fused halo push as between ranks — one
+        // kernel per slab per pass, edge planes stored straight into the neighbour's ghost plane over NVLink
+        for (auto &s : w->slabs) {
+            FS3D_CUDA(cudaSetDevice(s.device));
+            PairLayout L = pair_layout(s, hoff);
+            int rc = launch_skip_map(w, s);
+            if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, 1);
+            if (rc) return rc;
+        }
+        w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
     } else {
         // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
         for (auto &s : w->slabs) {
@@ -573,6 +585,32 @@ int fs3d_create(const fs3d_desc *desc, fs3d_world **out) {
     }
     rc = finish_create(w);
     if (rc) { std::string keep = g_err; fs3d_destroy(w); g_err = keep; return rc; }
+    // Slabs on distinct devices with peer access both ways use the fused halo push (kernels store into the
+    // neighbour's memory directly).  Slabs sharing a device keep the copy-based exchange: two persistent
+    // kernels on one device could wait on each other for SMs.
+    bool push_ok = n > 1 && !(desc->flags & FS3D_FLAG_NO_PEER_PUSH);
+    for (int i = 0; i < n && push_ok; ++i)
+        for (int j = 0; j < n && push_ok; ++j) {
+            if (i == j) continue;
+            if (w->devices[i] == w->devices[j]) push_ok = false;
+            if (std::abs(i - j) == 1) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, w->devices[i], w->devices[j]);
+                if (!can) push_ok = false;
+            }
+        }
+    if (push_ok) {
+        for (int i = 0; i < n; ++i) {
+            Slab &s = w->slabs[i];
+            if (i > 0) { Slab &d = w->slabs[i - 1]; s.peer_lo.buf[0] = d.buf[0]; s.peer_lo.buf[1] = d.buf[1]; s.peer_lo.flags = d.d_flags; s.peer_lo.nzl = d.nzl; s.peer_lo.valid = true; }
+            if (i + 1 < n) { Slab &d = w->slabs[i + 1]; s.peer_hi.buf[0] = d.buf[0]; s.peer_hi.buf[1] = d.buf[1]; s.peer_hi.flags = d.d_flags; s.peer_hi.nzl = d.nzl; s.peer_hi.valid = true; }
+        }
+        w->p2p = true;
+    }
+    if (n > 1) {   // ghost planes between slabs start as the neighbour's (EMPTY) edge plane, not as STONE
+        rc = refresh_ghosts(w);
+        if (rc) { std::string keep = g_err; fs3d_destroy(w); g_err = keep; return rc; }
+    }
     *out = w;
     return FS3D_OK;
 }
@@ -1066,6 +1104,7 @@ static int open_peer(Slab::Peer &pr, const void *blob, uint32_t expect_z, bool e
     FS3D_CUDA(cudaIpcOpenMemHandle((void **)&pr.flags, b.flags, cudaIpcMemLazyEnablePeerAccess));
     pr.nzl = b.nzl;
     pr.valid = true;
+    pr.ipc = true;
     return FS3D_OK;
 }
 

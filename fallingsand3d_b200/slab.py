@@ -157,6 +157,8 @@ class SlabWorld:
             self.engine.ipc_attach(lo, hi)
             dist.barrier(group=self.group)
             self.p2p = True
+        if self.world_size > 1:
+            self.refresh_halos()      # ghost planes between ranks start as the neighbour's (EMPTY) plane, not STONE
 
     # ---- halo exchange of one buffer (back = the buffer the current step is writing) ----
     def _exchange(self, back):

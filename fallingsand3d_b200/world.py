@@ -17,6 +17,7 @@ EMPTY, SAND, WATER, STONE = 0, 1, 2, 3
 SCENE_EMPTY, SCENE_SAND_BLOCK, SCENE_MIXED, SCENE_RANDOM, SCENE_MIXED_NOISE = 0, 1, 2, 3, 4
 FLAG_SKIP_SETTLED = 1
 FLAG_NO_FUSE = 2
+FLAG_NO_PEER_PUSH = 4
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",

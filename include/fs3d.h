@@ -59,6 +59,8 @@ extern "C" {
 /* fs3d_desc.flags */
 #define FS3D_FLAG_SKIP_SETTLED  1u   /* settled-tile skipping (bit-exact; SCHEDULE.md §4) */
 #define FS3D_FLAG_NO_FUSE       2u   /* one kernel pass per step (default: steps 2k, 2k+1 fuse into one pass) */
+#define FS3D_FLAG_NO_PEER_PUSH  4u   /* n_gpus > 1: exchange halos with peer copies on a side stream instead of
+                                        storing them from inside the step kernels (the default with peer access) */
 
 /* scene ids for fs3d_generate (SCHEDULE.md §5) */
 #define FS3D_SCENE_EMPTY        0

@@ -13,11 +13,15 @@ def _devices(n):
     return [i % k for i in range(n)]
 
 
-@pytest.mark.parametrize("nslabs,dims", [(2, (64, 16, 12)), (3, (256, 10, 13)), (4, (2048, 8, 16)), (2, (32, 6, 2))])
-def test_multislab_matches_oracle_and_single_slab(fs3d, oracle, nslabs, dims):
+# With >= nslabs GPUs the slabs sit on distinct devices and the kernels push their halos over peer memory
+# (the default); FLAG_NO_PEER_PUSH (and any world whose slabs share a device) uses peer copies instead.
+@pytest.mark.parametrize("flags", [0, 4])
+@pytest.mark.parametrize("nslabs,dims", [(2, (64, 16, 12)), (3, (256, 10, 13)), (4, (2048, 8, 16)), (2, (32, 6, 2)),
+                                         (2, (4096, 12, 10))])
+def test_multislab_matches_oracle_and_single_slab(fs3d, oracle, nslabs, dims, flags):
     nx, ny, nz = dims
     g = oracle.generate(nx, ny, nz, 3, 5)
-    with fs3d.VoxelWorld(nx, ny, nz, seed=9, devices=_devices(nslabs)) as w:
+    with fs3d.VoxelWorld(nx, ny, nz, seed=9, devices=_devices(nslabs), flags=flags) as w:
         assert w.num_slabs == nslabs
         w.upload(g)
         for t in range(12):
@@ -45,6 +49,19 @@ def test_multislab_async_pipelining_many_steps(fs3d, oracle):
         g[10, 60, 5] = 2
         w.step(30)
         oracle.run(g, 4, 60, 30)
+        assert np.array_equal(w.download(), g)
+
+
+def test_fresh_multislab_world_has_open_internal_boundaries(fs3d, oracle):
+    # no generate/upload: a grain dropped next to a slab boundary must see EMPTY (not a STONE ghost) across it
+    nx, ny, nz = 32, 12, 8
+    g = np.zeros((nz, ny, nx), np.uint8)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=3, devices=_devices(2)) as w:
+        for (x, y, z) in [(5, 10, 3), (6, 10, 3), (5, 11, 3), (7, 9, 4), (9, 10, 4)]:
+            w.set_cell(x, y, z, fs3d.SAND)
+            g[z, y, x] = 1
+        w.step(30)
+        oracle.run(g, 3, 0, 30)
         assert np.array_equal(w.download(), g)
 
 

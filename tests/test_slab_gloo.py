@@ -53,7 +53,7 @@ def test_slab_world_matches_whole_grid_oracle(oracle, world_size, dims, chunk):
         assert digests == want, f"rank {rank}"
         assert np.array_equal(whole, g)
         assert h == [int(v) for v in oracle.histogram(oracle.generate(nx, ny, nz, scene, 4))[:4]]
-        assert exchanges == passes + 1         # one per pass + the initial refresh
+        assert exchanges == passes + 2         # one per pass + the refresh at creation + the one after generate
     assert [o[4] for o in out] == slab_bounds(nz, world_size)
 
 
