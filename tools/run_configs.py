@@ -148,6 +148,7 @@ def config5():
     img = None
     for k in range(6):
         sw.step(10)
+        sw.sync()                          # the frame timer must not include the ten steps still in flight
         t1 = time.perf_counter()
         img = sw.raymarch(**cam)
         rm.append(time.perf_counter() - t1)
