@@ -117,6 +117,10 @@ static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
 #ifndef FS3D_HOST_CHUNK_MIB
 #define FS3D_HOST_CHUNK_MIB 256ull   // fs3d_step_host streams the grid in chunks of about this size (64 MiB measured 3 % slower)
 #endif
+// dynamic shared memory of a step kernel: only the staged-load experiment (-DFS3D_STAGE_LOADS=1) uses any
+static size_t step_smem(int jidx, int push) {
+    return (FS3D_STAGE_LOADS && !push && jidx >= 1) ? stage_smem_bytes<2, STEP_THREADS>() : 0;
+}
 constexpr uint32_t YTILE_LOG2 = 5, ZTILE_LOG2 = 3;   // activity tile = nx x 32 x 8 voxels
 
 static size_t plane_bytes(const fs3d_world *w) { return (size_t)w->desc.nx * w->desc.ny; }
@@ -150,7 +154,9 @@ static int init_slab(fs3d_world *w, Slab &s) {
                 for (int ox = 0; ox < 2; ++ox)
                     for (int td = 0; td < (ns == 2 ? 1 : 2); ++td) {
                         int nb = 0;
-                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), step_threads(w->jidx), 0));
+                        const size_t smem = step_smem(w->jidx, pu);
+                        if (smem) FS3D_CUDA(cudaFuncSetAttribute(step_fn(w->jidx, ox, td, sk, ns, pu), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), step_threads(w->jidx), smem));
                         s.blocks_per_sm[pu][ns - 1][sk][ox][td] = std::max(nb, 1);
                     }
     FS3D_CUDA(cudaMalloc(&s.d_flags, 2 * sizeof(unsigned long long)));
@@ -295,7 +301,7 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
         w->launches++;
         p.runs = s.d_runs; p.nruns = s.d_nruns;
     }
-    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, 0, s.s_main>>>(p);
+    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, step_smem(w->jidx, push), s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
     return FS3D_OK;

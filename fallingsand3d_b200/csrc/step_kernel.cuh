@@ -61,15 +61,22 @@ struct StepParams {
     unsigned long long wait_target;       // cumulative iterations the neighbours must have delivered
 };
 
+// cache-policy qualifiers of the streaming accesses (tuning hooks; defaults measured best)
+#ifndef FS3D_LD_POLICY
+#define FS3D_LD_POLICY ".L1::no_allocate"
+#endif
+#ifndef FS3D_ST_POLICY
+#define FS3D_ST_POLICY ".L1::no_allocate"
+#endif
 __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t (&r)[8]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" FS3D_LD_POLICY ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
 // same, through the coherent path: ghost planes are written by a peer GPU while this kernel runs.
 // (asm volatile statements keep their program order, so these stay behind the acquire of the arrival flag.)
 __device__ __forceinline__ void ld256_coherent(const uint8_t *p, uint32_t (&r)[8]) {
-    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" FS3D_LD_POLICY ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
@@ -79,10 +86,41 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 __device__ __forceinline__ void st256(uint8_t *p, const uint32_t (&r)[8]) {
-    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+    asm volatile("st.global" FS3D_ST_POLICY ".v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+
+// ---- experiment: bulk-async (TMA engine) staging of the row segments in a per-warp shared-memory ring ----
+// -DFS3D_STAGE_LOADS=1 replaces the LDG register double-buffering of the J = 2, non-PUSH kernels by
+// cp.async.bulk copies (2 KiB per row-plane) completing on an mbarrier, FS3D_NSTAGE plane pairs deep.
+#ifndef FS3D_STAGE_LOADS
+#define FS3D_STAGE_LOADS 0
+#endif
+#ifndef FS3D_NSTAGE
+#define FS3D_NSTAGE 2
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void lds256(uint32_t addr, uint32_t (&r)[8]) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr + 16u));
+}
+template <int J, int THREADS>
+constexpr uint32_t stage_smem_bytes() { return (THREADS / 32) * FS3D_NSTAGE * (4u * J * 1024u) + (THREADS / 32) * FS3D_NSTAGE * 8u; }
 
 template <int J>
 struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u32]
@@ -134,6 +172,19 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     if (XCH) {
         if (threadIdx.x < PAIRS * 4) xch_smem[threadIdx.x] = 0u;   // tag 0 is never expected first
         __syncthreads();
+    }
+
+    // staging ring (experiment): [warp][stage][row][plane][J KiB] then one mbarrier per warp and stage
+    constexpr bool STG = FS3D_STAGE_LOADS && !PUSH && J == 2;
+    constexpr uint32_t ROWB = J * 1024u, STAGE_BYTES = 4u * ROWB;
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    const uint32_t ring = STG ? smem_u32(dyn_smem) + wic * (FS3D_NSTAGE * STAGE_BYTES) : 0u;
+    const uint32_t bars = STG ? smem_u32(dyn_smem) + (THREADS / 32) * (FS3D_NSTAGE * STAGE_BYTES) + wic * (FS3D_NSTAGE * 8u) : 0u;
+    uint32_t kc = 0, ki = 0;                       // stages consumed / issued so far (ring position and phase)
+    if (STG) {
+        if (lane == 0) for (int st = 0; st < FS3D_NSTAGE; ++st) mbar_init(bars + 8u * st, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
     }
 
     uint32_t g = 0, xw0 = lane + half * (32u * J);
@@ -246,6 +297,41 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                     }
         };
 
+        // staged variant: lane 0 asks the copy engine for this warp's four row-plane segments of plane pair `it`
+        const uint32_t seg_w = (pair_ok && p.wpr > half * (32u * J)) ? (p.wpr - half * (32u * J) < 32u * J ? p.wpr - half * (32u * J) : 32u * J) : 0u;
+        const uint32_t seg_bytes = seg_w * 32u;
+        const uint8_t *seg_src = p.src + (size_t)lzl * plane_rows * row_bytes + (size_t)half * (32u * J) * 32u;
+        auto issue_pair = [&](uint32_t it) {
+            if (lane == 0) {
+                const uint32_t st = ki % FS3D_NSTAGE, bar = bars + 8u * st;
+                mbar_expect_tx(bar, 4u * seg_bytes);
+                if (seg_bytes) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t y = 2u * it + h;
+                            bulk_g2s(ring + st * STAGE_BYTES + (uint32_t)(r * 2 + h) * ROWB,
+                                     seg_src + (size_t)r * plane_rows * row_bytes + (size_t)(y < ylast ? y : ylast) * row_bytes,
+                                     seg_bytes, bar);
+                        }
+                }
+            }
+            ++ki;
+        };
+        auto consume_pair = [&]() {
+            const uint32_t st = kc % FS3D_NSTAGE;
+            mbar_wait(bars + 8u * st, (kc / FS3D_NSTAGE) & 1u);
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        lds256(ring + st * STAGE_BYTES + (uint32_t)(r * 2 + h) * ROWB + (lane + 32u * j) * 32u, raw.w[j][r][h]);
+            ++kc;
+        };
+
         P2 prev1[J][2], c2[J][2], c3[J][2], lo[J][2], hi[J][2];
         auto reset_carry = [&]() {
 #pragma unroll
@@ -345,8 +431,10 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                 warm = it < LEAD ? it : LEAD;
                 it -= warm;
                 need_restart = false; loaded = false;
+                if (STG) for (uint32_t a = it; a < it_b && a < it + FS3D_NSTAGE; ++a) issue_pair(a);
             }
-            if (!loaded) load_pair(it);
+            if (STG) consume_pair();
+            else if (!loaded) load_pair(it);
 
             const uint32_t y1 = 2u * it;
 #pragma unroll
@@ -361,8 +449,15 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
 
             // the next iteration's loads are in flight while this one is evaluated
             const uint32_t nxt = it + 1;
-            loaded = nxt < it_b;
-            if (loaded) load_pair(nxt);
+            if (STG) {
+                // the words are in registers: hand the stage back to the copy engine for plane pair it + NSTAGE
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (it + FS3D_NSTAGE < it_b) issue_pair(it + FS3D_NSTAGE);
+            } else {
+                loaded = nxt < it_b;
+                if (loaded) load_pair(nxt);
+            }
 
             uint32_t e1, e2, e3 = 0, e4 = 0;
             if (TODD == 0) { e1 = do_xy(hi, lo, y1 + 1, p.key_xy); e2 = do_zy(lo, prev1, y1, p.key_zy); }

@@ -200,6 +200,24 @@ class SlabWorld:
     def download(self):
         return self.engine.download()
 
+    # ---- checkpoint: one file per rank (format in include/fs3d.h) ----
+    def rank_path(self, path):
+        return f"{path}.z{self.z_begin}-{self.z_end}"
+
+    def save(self, path):
+        """Every rank writes its slab to rank_path(path)."""
+        self.engine.world.save(self.rank_path(path))
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+
+    def load(self, path):
+        """Every rank restores its slab, step index and seed from rank_path(path); halos are refreshed."""
+        self.engine.world.load(self.rank_path(path))
+        self.step_index = self.engine.world.step_index
+        self.seed = self.engine.world.seed
+        if self.world_size > 1:
+            self.refresh_halos()
+
     def step(self, n=1):
         if self.p2p:
             self.engine.world.step(int(n))      # the library loops; halos move inside the kernels

@@ -61,6 +61,26 @@ def main():
             if rank == 0 and not np.array_equal(img, ref.raymarch(**cam)):
                 ok = False
                 print(f"MISMATCH {nx}x{ny}x{nz} p2p={p2p} raymarch composite", flush=True)
+        # per-rank checkpoints: save, run on, load, run on again -> same digest as the uninterrupted run
+        import tempfile
+        base = [tempfile.mkdtemp(prefix="fs3d_ckpt_") if rank == 0 else None]
+        dist.broadcast_object_list(base, src=0)
+        ck = os.path.join(base[0], "w")
+        sw.save(ck)
+        t_saved = sw.step_index
+        sw.step(5)
+        d_after = sw.digest()
+        sw.step(3)
+        sw.load(ck)
+        if sw.step_index != t_saved:
+            ok = False
+        sw.step(5)
+        if sw.digest() != d_after:
+            ok = False
+            print(f"MISMATCH {nx}x{ny}x{nz} p2p={p2p} after checkpoint resume", flush=True)
+        if rank == 0:
+            ref.step(5)
+            ok = ok and ref.digest() == d_after
         h = sw.histogram()
         if rank == 0:
             ok = ok and np.array_equal(h, ref.histogram())

@@ -101,3 +101,23 @@ def test_cpp_engine_loop_runs_on_the_gpu(fs3d, tmp_path):
     assert res.returncode == 0, res.stdout + res.stderr
     assert "steps 100" in res.stdout and "sand 4096 -> 4096" in res.stdout
     assert os.path.getsize(tmp_path / "frame_100.ppm") == len("P6\n850 450\n255\n") + 850 * 450 * 3
+
+
+def test_header_is_plain_c99(tmp_path):
+    # the boundary is a C ABI: include/fs3d.h must compile as C (not only C++), and the constants the
+    # file format and the bindings rely on must have the documented values
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text("""
+#include <stddef.h>
+#include "fs3d.h"
+_Static_assert(FS3D_CKPT_HEADER_BYTES == 80, "checkpoint header");
+_Static_assert(FS3D_IPC_BLOB_BYTES == 256, "ipc blob");
+_Static_assert(sizeof(fs3d_camera) == 20, "camera: pos[3], yaw, aspect");
+_Static_assert(offsetof(fs3d_view, pitch_y) == 32 && sizeof(fs3d_view) == 56, "view layout used by _lib.View");
+_Static_assert(offsetof(fs3d_desc, seed) == 16 && offsetof(fs3d_desc, devices) == 32 && sizeof(fs3d_desc) == 48, "desc layout used by _lib.Desc");
+int use(fs3d_world *w) { uint64_t s = 0; return fs3d_step(w, 1) + fs3d_step_index(w, &s) + fs3d_save(w, "x"); }
+""")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                          "-c", str(src), "-o", str(tmp_path / "abi.o")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
