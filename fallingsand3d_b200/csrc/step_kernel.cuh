@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     const uint32_t half = FS3D_EXP_PAIR_SPLIT ? wic / PAIRS : wic % XW;  // which 32·J-word half of the row this warp owns
     const uint32_t gw = blockIdx.x * PAIRS + pic; // work unit (z-pair marcher): one warp, or a warp pair
     const uint32_t nw = gridDim.x * PAIRS;
-    __shared__ uint32_t xch_smem[XCH ? PAIRS * 4 : 1];   // [pair in CTA][parity][from half]
+    __shared__ uint32_t xch_smem[XCH ? PAIRS * 4 : 1];   // [pair in CTA][mailboxes]
     volatile uint32_t *const xch = xch_smem + (XCH ? pic * 4 : 0);
     uint32_t xseq = 0;                             // exchanges done; both warps of a pair count alike
     if (XCH) {
@@ -340,35 +340,67 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                 for (int r = 0; r < 2; ++r) { prev1[j][r] = {ONES, ONES}; c2[j][r] = {ONES, ONES}; c3[j][r] = {ONES, ONES}; }
         };
 
-        // XY sub-step on (upper, lower) for both rows, upper row is plane yu
+        // Odd x-offset has two implementations of the XY sub-step (even offset always uses xy_pair_substep0):
+        //   pair  (xy_pair_substep1): every block evaluated once, ~30 % fewer ALU instructions and 15-35 fewer
+        //         registers, but two dependent shuffle round trips per sub-step (next word's cells in, new voxel 0 back);
+        //   column (xy_substep): every block evaluated from both columns, one round trip.
+        // Measured on one box (profiles/r01d_experiments_xy_pair.txt): the pair form wins where issue slots or
+        // registers are the limit (single-step kernels 1 %, warp-pair PUSH kernels 8 %, sparse SKIP passes 10 %), the
+        // column form where two warps per scheduler must hide the extra round trip (fused XW = 1 kernels, 5 %).
+        // -DFS3D_XY_PAIR_OX1=0/1 forces one of them everywhere.
+#ifdef FS3D_XY_PAIR_OX1
+        constexpr bool PAIR1 = FS3D_XY_PAIR_OX1 != 0;
+#else
+        constexpr bool PAIR1 = NS == 1 || XW == 2 || SKIP == 1;
+#endif
+        // One-way message between the two warps of a pair (XW = 2): a tagged 32-bit mailbox in shared memory.
+        // Both warps count messages alike; messages alternate direction (pre: half 1 -> 0, post: half 0 -> 1),
+        // so message k + 2 reuses the slot of message k only after its reader has answered message k + 1.
+        auto xmail = [&](uint32_t from_half, uint32_t from_lane, uint32_t payload) -> uint32_t {
+            ++xseq;
+            const uint32_t tag = (xseq & 0x3FFFu) << 18;
+            volatile uint32_t *slot = xch + (xseq & 1u);
+            if (half == from_half) {
+                if (lane == from_lane) *slot = tag | payload;
+                return 0u;
+            }
+            uint32_t v;
+            do { v = *slot; } while ((v & 0xFFFC0000u) != tag);
+            return v & 0x3FFFFu;
+        };
+        // XY sub-step on (upper, lower) of both rows at once, every block evaluated once (bitslice.cuh,
+        // xy_pair_substep*); the upper row is plane yu
         auto do_xy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu, uint32_t key) {
             uint32_t en = 0;
-            uint32_t rw[J][2], e[J][2];
-            uint32_t xin[2] = {EDGE_STONE, EDGE_STONE};
+            uint32_t rw[J][2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int j = 0; j < J; ++j)
 #pragma unroll
-                for (int j = 0; j < J; ++j) {
-                    rw[j][r] = hash_word(key + hxy[j][r] + yu * HC2);
-                    if (OX == 1) e[j][r] = edge_pack(up[j][r], lw[j][r], rw[j][r]);
+                for (int r = 0; r < 2; ++r) rw[j][r] = hash_word(key + hxy[j][r] + yu * HC2);
+            if (OX == 0) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) en |= xy_pair_substep0(up[j][0], lw[j][0], up[j][1], lw[j][1], rw[j][0], rw[j][1]);
+            } else if (!PAIR1) {
+                // per-column evaluation (xy_substep): one exchange of edge words, every block computed from both columns
+                uint32_t e[J][2];
+                uint32_t xe[2] = {EDGE_STONE, EDGE_STONE};
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int j = 0; j < J; ++j) e[j][r] = edge_pack(up[j][r], lw[j][r], rw[j][r]);
+                if (XCH) {
+                    ++xseq;
+                    const uint32_t tag = (xseq & 0x3FFFu) << 18;
+                    volatile uint32_t *slot = xch + (xseq & 1u) * 2u;
+                    const uint32_t mine = half == 0u ? (e[J - 1][0] | (e[J - 1][1] << 9)) : (e[0][0] | (e[0][1] << 9));
+                    if (lane == (half == 0u ? 31u : 0u)) slot[half] = tag | mine;
+                    uint32_t v;
+                    do { v = slot[half ^ 1u]; } while ((v & 0xFFFC0000u) != tag);
+                    xe[0] = v & 0x1FFu;
+                    xe[1] = (v >> 9) & 0x1FFu;
                 }
-            if (XCH) {
-                // mailbox word = tag(14) | row-1 edge(9) | row-0 edge(9).  Slots alternate by parity: when I
-                // write exchange k + 2 I have seen the partner's k + 1, which it wrote after reading my k.
-                ++xseq;
-                const uint32_t tag = (xseq & 0x3FFFu) << 18;
-                volatile uint32_t *slot = xch + (xseq & 1u) * 2u;
-                const uint32_t mine = half == 0u ? (e[J - 1][0] | (e[J - 1][1] << 9)) : (e[0][0] | (e[0][1] << 9));
-                if (lane == (half == 0u ? 31u : 0u)) slot[half] = tag | mine;
-                uint32_t v;
-                do { v = slot[half ^ 1u]; } while ((v & 0xFFFC0000u) != tag);
-                xin[0] = v & 0x1FFu;
-                xin[1] = (v >> 9) & 0x1FFu;
-            }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                uint32_t ep[J], enx[J];
-                if (OX == 1) {
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
                     for (int j = 0; j < J; ++j) {
                         uint32_t a = __shfl_up_sync(ONES, e[j][r], 1);
@@ -377,17 +409,39 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                             if (j > 0)     { uint32_t t = __shfl_sync(ONES, e[j - 1][r], 31); if (lane == 0)  a = t; }
                             if (j < J - 1) { uint32_t t = __shfl_sync(ONES, e[j + 1][r], 0);  if (lane == 31) b = t; }
                         }
-                        if (XCH && j == 0     && half == 1u && lane == 0u)  a = xin[r];
-                        if (XCH && j == J - 1 && half == 0u && lane == 31u) b = xin[r];
-                        ep[j]  = hasp[j] ? a : EDGE_STONE;
-                        enx[j] = hasn[j] ? b : EDGE_STONE;
+                        if (XCH && j == 0     && half == 1u && lane == 0u)  a = xe[r];
+                        if (XCH && j == J - 1 && half == 0u && lane == 31u) b = xe[r];
+                        en |= xy_substep<1>(up[j][r], lw[j][r], rw[j][r], hasp[j] ? a : EDGE_STONE, hasn[j] ? b : EDGE_STONE);
                     }
-                } else {
+            } else {
+                // blocks (4k+3, 4k+4) straddle words: a lane evaluates the blocks whose LEFT cell it owns.
+                // pre: the next word's voxel-0 bits (shuffle down); post: the new voxel 0 from the previous word's
+                // evaluation (shuffle up) or, at the grid wall, the fall-only rule
+                uint32_t first[J], carry[J];
 #pragma unroll
-                    for (int j = 0; j < J; ++j) { ep[j] = EDGE_STONE; enx[j] = EDGE_STONE; }
+                for (int j = 0; j < J; ++j) first[j] = xy_first_bits(up[j][0], lw[j][0], up[j][1], lw[j][1]);
+                uint32_t xin = 0xFFu;
+                if (XCH) xin = xmail(1u, 0u, first[0]);
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    uint32_t b = __shfl_down_sync(ONES, first[j], 1);
+                    if (J > 1 && j < J - 1) { uint32_t t = __shfl_sync(ONES, first[j + 1], 0); if (lane == 31) b = t; }
+                    if (XCH && j == J - 1 && half == 0u && lane == 31u) b = xin;
+                    en |= xy_pair_substep1(up[j][0], lw[j][0], up[j][1], lw[j][1], rw[j][0], rw[j][1], hasn[j] ? b : 0xFFu, carry[j]);
                 }
+                if (XCH) xin = xmail(0u, 31u, carry[J - 1]);
 #pragma unroll
-                for (int j = 0; j < J; ++j) en |= xy_substep<OX>(up[j][r], lw[j][r], rw[j][r], ep[j], enx[j]);
+                for (int j = 0; j < J; ++j) {
+                    uint32_t a = __shfl_up_sync(ONES, carry[j], 1);
+                    if (J > 1 && j > 0) { uint32_t t = __shfl_sync(ONES, carry[j - 1], 31); if (lane == 0) a = t; }
+                    if (XCH && j == 0 && half == 1u && lane == 0u) a = xin;
+                    if (j == 0) {           // only a row's first word can sit at the wall
+                        uint32_t enw = 0;
+                        const uint32_t wall = xy_wall_first(first[0], enw);
+                        if (!hasp[0]) { a = wall; en |= enw; }
+                    }
+                    xy_pair_post1(up[j][0], lw[j][0], up[j][1], lw[j][1], a);
+                }
             }
             return en;
         };

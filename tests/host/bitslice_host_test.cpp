@@ -95,6 +95,33 @@ static void emu_xy(Grid &g, uint32_t key, int oy) {
             }
         }
 }
+// the same sub-step through the pair functions (every block evaluated once, rows taken two at a time)
+template <int OX>
+static void emu_xy_pair(Grid &g, uint32_t key, int oy) {
+    for (int z = 0; z < g.nz; z += 2)
+        for (int y0 = oy ? -1 : 0; y0 < g.ny; y0 += 2) {
+            const int W = g.wpr;
+            std::vector<P2> U0(W), L0(W), U1(W), L1(W); std::vector<uint32_t> r0(W), r1(W), first(W), carry(W);
+            for (int xw = 0; xw < W; ++xw) {
+                U0[xw] = rdw(g, z, y0 + 1, xw); L0[xw] = rdw(g, z, y0, xw); U1[xw] = rdw(g, z + 1, y0 + 1, xw); L1[xw] = rdw(g, z + 1, y0, xw);
+                r0[xw] = hash_word(key + (uint32_t)xw * HC1 + (uint32_t)(y0 + 1) * HC2 + (uint32_t)z * HC3);
+                r1[xw] = hash_word(key + (uint32_t)xw * HC1 + (uint32_t)(y0 + 1) * HC2 + (uint32_t)(z + 1) * HC3);
+                first[xw] = xy_first_bits(U0[xw], L0[xw], U1[xw], L1[xw]);
+            }
+            for (int xw = 0; xw < W; ++xw) {
+                if (OX == 0) xy_pair_substep0(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw]);
+                else xy_pair_substep1(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw], xw + 1 < W ? first[xw + 1] : 0xFFu, carry[xw]);
+            }
+            if (OX == 1)
+                for (int xw = 0; xw < W; ++xw) {
+                    uint32_t en = 0;
+                    xy_pair_post1(U0[xw], L0[xw], U1[xw], L1[xw], xw > 0 ? carry[xw - 1] : xy_wall_first(first[0], en));
+                }
+            for (int xw = 0; xw < W; ++xw) {
+                wrw(g, z, y0 + 1, xw, U0[xw]); wrw(g, z, y0, xw, L0[xw]); wrw(g, z + 1, y0 + 1, xw, U1[xw]); wrw(g, z + 1, y0, xw, L1[xw]);
+            }
+        }
+}
 static void emu_zy(Grid &g, uint32_t key, int oz, int oy) {
     for (int z0 = oz ? -1 : 0; z0 < g.nz; z0 += 2)
         for (int y0 = oy ? -1 : 0; y0 < g.ny; y0 += 2)
@@ -106,8 +133,9 @@ static void emu_zy(Grid &g, uint32_t key, int oz, int oy) {
             }
 }
 
-// usage: prog                      -> unit tests
-//        prog nx ny nz kxy kzy t   -> reads nx*ny*nz bytes on stdin, writes one emulated step to stdout
+// usage: prog                          -> unit tests
+//        prog nx ny nz kxy kzy t [p]   -> reads nx*ny*nz bytes on stdin, writes one emulated step to stdout
+//                                         (p = 1: XY through the pair functions the kernel uses)
 int main(int argc, char **argv) {
     if (argc < 7) {
         int bad = unit_tests();
@@ -122,8 +150,13 @@ int main(int argc, char **argv) {
     g.w.resize((size_t)g.nz * g.ny * g.wpr);
     for (size_t i = 0; i < g.w.size(); ++i) { uint32_t w[8]; memcpy(w, &bytes[i * 32], 32); g.w[i] = pack(w); }
     int hoff = (t >> 1) & 1;
-    if ((t & 1) == 0) { if (hoff) emu_xy<1>(g, kxy, 0); else emu_xy<0>(g, kxy, 0); emu_zy(g, kzy, hoff, 1); }
-    else              { emu_zy(g, kzy, hoff, 0); if (hoff) emu_xy<1>(g, kxy, 1); else emu_xy<0>(g, kxy, 1); }
+    const bool pairfn = argc > 7 && atoi(argv[7]) != 0;   // 1: xy_pair_substep* (what the kernel runs), 0: xy_substep
+    auto xy = [&](int oy) {
+        if (pairfn) { if (hoff) emu_xy_pair<1>(g, kxy, oy); else emu_xy_pair<0>(g, kxy, oy); }
+        else        { if (hoff) emu_xy<1>(g, kxy, oy); else emu_xy<0>(g, kxy, oy); }
+    };
+    if ((t & 1) == 0) { xy(0); emu_zy(g, kzy, hoff, 1); }
+    else              { emu_zy(g, kzy, hoff, 0); xy(1); }
     for (size_t i = 0; i < g.w.size(); ++i) { uint32_t w[8]; unpack(g.w[i], w); memcpy(&bytes[i * 32], w, 32); }
     fwrite(bytes.data(), 1, bytes.size(), stdout);
     return 0;

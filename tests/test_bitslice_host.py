@@ -23,13 +23,16 @@ def test_helper_units(exe):
     assert res.returncode == 0 and "bad=0" in res.stdout
 
 
-@pytest.mark.parametrize("dims", [(32, 8, 6), (64, 9, 5), (96, 7, 3), (128, 16, 4)])
-def test_word_level_emulation_matches_oracle(exe, oracle, dims):
+@pytest.mark.parametrize("pairfn", [0, 1])
+@pytest.mark.parametrize("dims", [(32, 8, 6), (64, 9, 5), (96, 7, 3), (128, 16, 4), (32, 5, 1)])
+def test_word_level_emulation_matches_oracle(exe, oracle, dims, pairfn):
+    # pairfn = 1: the XY sub-step through xy_pair_substep0/1 (each block evaluated once, both rows of a
+    # z-pair per call) — the functions the kernel runs; pairfn = 0: the per-column xy_substep
     nx, ny, nz = dims
     g = oracle.generate(nx, ny, nz, 3, 5)
     for t in range(8):
         kxy, kzy = oracle.key(7, t, 0), oracle.key(7, t, 1)
-        out = subprocess.run([exe, str(nx), str(ny), str(nz), str(kxy), str(kzy), str(t)], input=g.tobytes(),
+        out = subprocess.run([exe, str(nx), str(ny), str(nz), str(kxy), str(kzy), str(t), str(pairfn)], input=g.tobytes(),
                              capture_output=True, check=True).stdout
         e = np.frombuffer(out, dtype=np.uint8).reshape(g.shape)
         oracle.step(g, 7, t)
