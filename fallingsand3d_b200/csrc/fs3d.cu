@@ -27,10 +27,16 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 #ifndef FS3D_STEP_THREADS
 #define FS3D_STEP_THREADS 256
 #endif
-constexpr int STEP_THREADS = FS3D_STEP_THREADS;
-static int step_threads(int) { return STEP_THREADS; }
-// kernel shapes by row width: jidx 0: J = 1 (nx <= 1024), 1: J = 2 (nx <= 2048), 2: J = 2 x 2 warps (nx <= 4096)
+constexpr int STEP_THREADS = FS3D_STEP_THREADS;         // J = 2 kernels (nx > 1024)
+#ifndef FS3D_STEP_THREADS_J1
+#define FS3D_STEP_THREADS_J1 384   // 12 warps per SM: 4.5 % faster than 256 x 2 CTAs at 1024^3 (profiles/r01d_experiments_xy_pair.txt)
+#endif
+constexpr int STEP_THREADS_J1 = FS3D_STEP_THREADS_J1;   // J = 1 kernels (nx <= 1024) on grids large enough to be bandwidth-bound
+// kernel shapes: jidx 0: J = 1 (nx <= 1024), 1: J = 2 (nx <= 2048), 2: J = 2 x 2 warps (nx <= 4096),
+//                3: J = 1 in STEP_THREADS-sized CTAs — small grids are launch/latency-bound and ran 15 % slower in 384-thread CTAs
+static int step_threads(int jidx) { return jidx == 0 ? STEP_THREADS_J1 : STEP_THREADS; }
 static uint32_t warps_per_pair(int jidx) { return jidx == 2 ? 2u : 1u; }
+constexpr uint64_t SMALL_GRID_VOXELS = 1ull << 27;      // per slab; 512^3 measured the same either way
 
 struct Slab {
     int device = 0;
@@ -83,7 +89,7 @@ struct fs3d_world {
     bool external = false;       // created by fs3d_create_slab: caller exchanges halos
     bool halo_pending = false;   // in-process: ghost planes of `cur` are being filled on s_comm
     uint64_t launches = 0;       // kernels launched since creation
-    int jidx = 0;                // 0: J=1, 1: J=2, 2: J=4
+    int jidx = 0;                // kernel shape, see step_threads()
     uint32_t lpr = 32, groups = 1;
     bool palette_dirty = true;
     float palette[256 * 4];
@@ -97,18 +103,23 @@ namespace fs3d {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
 typedef void (*StepFn)(const StepParams);
+#define FS3D_TH(J) ((J) == 1 ? STEP_THREADS_J1 : STEP_THREADS)
 #define FS3D_ROW(J, XW, SK, PU) \
+    {{step_kernel<J, XW, 0, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, XW, 0, 1, SK, 1, PU, FS3D_TH(J)>}, \
+     {step_kernel<J, XW, 1, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, XW, 1, 1, SK, 1, PU, FS3D_TH(J)>}}
+#define FS3D_ROW2(J, XW, SK, PU) {step_kernel<J, XW, 0, 0, SK, 2, PU, FS3D_TH(J)>, step_kernel<J, XW, 1, 0, SK, 2, PU, FS3D_TH(J)>}
+#define FS3D_ROW_S(J, XW, SK, PU) \
     {{step_kernel<J, XW, 0, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, XW, 0, 1, SK, 1, PU, STEP_THREADS>}, \
      {step_kernel<J, XW, 1, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, XW, 1, 1, SK, 1, PU, STEP_THREADS>}}
-#define FS3D_ROW2(J, XW, SK, PU) {step_kernel<J, XW, 0, 0, SK, 2, PU, STEP_THREADS>, step_kernel<J, XW, 1, 0, SK, 2, PU, STEP_THREADS>}
-#define FS3D_SHAPES(M, SK, PU) {M(1, 1, SK, PU), M(2, 1, SK, PU), M(2, 2, SK, PU)}
+#define FS3D_ROW2_S(J, XW, SK, PU) {step_kernel<J, XW, 0, 0, SK, 2, PU, STEP_THREADS>, step_kernel<J, XW, 1, 0, SK, 2, PU, STEP_THREADS>}
+#define FS3D_SHAPES(M, SK, PU) {M(1, 1, SK, PU), M(2, 1, SK, PU), M(2, 2, SK, PU), M##_S(1, 1, SK, PU)}
 // ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even; push = fused halo push over peer memory
 static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
-    static StepFn tab1[2][2][3][2][2] = {
+    static StepFn tab1[2][2][4][2][2] = {
         {FS3D_SHAPES(FS3D_ROW, 0, 0), FS3D_SHAPES(FS3D_ROW, 1, 0)},
         {FS3D_SHAPES(FS3D_ROW, 0, 1), FS3D_SHAPES(FS3D_ROW, 1, 1)},
     };
-    static StepFn tab2[2][2][3][2] = {
+    static StepFn tab2[2][2][4][2] = {
         {FS3D_SHAPES(FS3D_ROW2, 0, 0), FS3D_SHAPES(FS3D_ROW2, 1, 0)},
         {FS3D_SHAPES(FS3D_ROW2, 0, 1), FS3D_SHAPES(FS3D_ROW2, 1, 1)},
     };
@@ -119,7 +130,7 @@ static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
 #endif
 // dynamic shared memory of a step kernel: only the staged-load experiment (-DFS3D_STAGE_LOADS=1) uses any
 static size_t step_smem(int jidx, int push) {
-    return (FS3D_STAGE_LOADS && !push && jidx >= 1) ? stage_smem_bytes<2, STEP_THREADS>() : 0;
+    return (FS3D_STAGE_LOADS && !push && (jidx == 1 || jidx == 2)) ? stage_smem_bytes<2, STEP_THREADS>() : 0;
 }
 constexpr uint32_t YTILE_LOG2 = 5, ZTILE_LOG2 = 3;   // activity tile = nx x 32 x 8 voxels
 
@@ -229,6 +240,9 @@ static int finish_create(fs3d_world *w) {
     w->jidx = wpr <= 32 ? 0 : (wpr <= 64 ? 1 : 2);
     w->lpr = wpr < 32 ? wpr : 32;
     w->groups = w->jidx == 0 ? 32 / w->lpr : 1;
+    uint64_t slab_voxels = 0;
+    for (auto &s : w->slabs) slab_voxels = std::max<uint64_t>(slab_voxels, (uint64_t)w->desc.nx * w->desc.ny * s.nzl);
+    if (w->jidx == 0 && slab_voxels < SMALL_GRID_VOXELS) w->jidx = 3;
     default_palette(w->palette);
     for (auto &s : w->slabs) { int rc = init_slab(w, s); if (rc) return rc; }
     return FS3D_OK;
