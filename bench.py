@@ -235,7 +235,7 @@ def ours(args):
         if rank == 0:
             sampler.start()
             sampler.wait_ready()
-        sw.step(Wm)
+        sw.step(Wm + (Wm & 1))          # same (even) warm-up as at N = 1, so the digest is comparable across N
         sw.sync()
         dist.barrier()
         torch.cuda.synchronize()
