@@ -1252,6 +1252,18 @@ struct CkptHeader {
 };
 static_assert(sizeof(CkptHeader) == FS3D_CKPT_HEADER_BYTES, "checkpoint header layout is part of the file format");
 
+namespace {
+struct File {          // closes on every return path
+    FILE *f = nullptr;
+    ~File() { if (f) std::fclose(f); }
+    int close() { const int r = f ? std::fclose(f) : 0; f = nullptr; return r; }
+};
+struct DevBuf {        // frees on every return path (on whatever device is current: set it before the scope ends)
+    uint32_t *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
 int fs3d_save(fs3d_world *w, const char *path) {
     if (!w || !path) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
     uint64_t dg = 0;
@@ -1265,56 +1277,54 @@ int fs3d_save(fs3d_world *w, const char *path) {
     h.nx = w->desc.nx; h.ny = w->desc.ny; h.nz = w->desc.nz; h.z_begin = zb; h.z_end = ze;
     h.encoding = 1; h.step = w->step; h.seed = w->desc.seed; h.digest = dg;
     h.payload_bytes = pb / 4 * (uint64_t)(ze - zb);      // nx % 32 == 0, so a plane packs to whole bytes
-    FILE *f = std::fopen(path, "wb");
-    if (!f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path + " for writing");
-    bool io_ok = std::fwrite(&h, sizeof(h), 1, f) == 1;
+    File out;
+    out.f = std::fopen(path, "wb");
+    if (!out.f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path + " for writing");
+    bool io_ok = std::fwrite(&h, sizeof(h), 1, out.f) == 1;
     // pack on the device, stream to the file in chunks of whole planes (<= ~64 MiB packed)
     const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / 4));
     std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / 4));
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
-        uint32_t *d_packed = nullptr;
+        DevBuf packed;
         const uint32_t cp = std::min(planes_per_chunk, s.nzl);
-        cudaError_t e = cudaMalloc(&d_packed, (size_t)cp * (pb / 4));
-        if (e != cudaSuccess) { std::fclose(f); FS3D_CUDA(e); }
+        FS3D_CUDA(cudaMalloc(&packed.p, (size_t)cp * (pb / 4)));
         for (uint32_t z = 0; z < s.nzl && io_ok; z += cp) {
             const uint32_t n = std::min(cp, s.nzl - z);
             const uint64_t n16 = pb * n / 16;
-            pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur) + pb * z, n16, d_packed);
-            e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaMemcpyAsync(host.data(), d_packed, n16 * 4, cudaMemcpyDeviceToHost, s.s_main);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
-            if (e != cudaSuccess) { cudaFree(d_packed); std::fclose(f); FS3D_CUDA(e); }
+            pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur) + pb * z, n16, packed.p);
+            FS3D_CUDA(cudaGetLastError());
             w->launches++;
-            io_ok = std::fwrite(host.data(), 1, n16 * 4, f) == n16 * 4;
+            FS3D_CUDA(cudaMemcpyAsync(host.data(), packed.p, n16 * 4, cudaMemcpyDeviceToHost, s.s_main));
+            FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+            io_ok = std::fwrite(host.data(), 1, n16 * 4, out.f) == n16 * 4;
         }
-        cudaFree(d_packed);
     }
-    io_ok = (std::fclose(f) == 0) && io_ok;
+    io_ok = (out.close() == 0) && io_ok;
     if (!io_ok) return fail(FS3D_ERR_IO, std::string("short write to ") + path);
     return FS3D_OK;
 }
 
 int fs3d_load(fs3d_world *w, const char *path) {
     if (!w || !path) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
-    FILE *f = std::fopen(path, "rb");
-    if (!f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path);
+    File in;
+    in.f = std::fopen(path, "rb");
+    if (!in.f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path);
     CkptHeader h{};
-    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "FS3DCKPT", 8) != 0) {
-        std::fclose(f);
+    if (std::fread(&h, sizeof(h), 1, in.f) != 1 || std::memcmp(h.magic, "FS3DCKPT", 8) != 0)
         return fail(FS3D_ERR_IO, std::string(path) + " is not an fs3d checkpoint");
-    }
     const size_t pb = plane_bytes(w);
     const uint32_t zb = w->slabs.front().z0, ze = w->slabs.back().z0 + w->slabs.back().nzl;
-    std::string why;
-    if (h.format_version != FS3D_CKPT_VERSION || h.encoding != 1) why = "unknown checkpoint format version / encoding";
-    else if (h.schedule_version != FS3D_SCHEDULE_VERSION) why = "checkpoint was written under another schedule version";
-    else if (h.nx != w->desc.nx || h.ny != w->desc.ny || h.nz != w->desc.nz) why = "checkpoint grid differs from the world's";
-    else if (h.z_begin != zb || h.z_end != ze) why = "checkpoint holds other z-planes than this world";
-    else if (h.payload_bytes != pb / 4 * (uint64_t)(ze - zb)) why = "checkpoint payload size is inconsistent";
-    if (!why.empty()) { std::fclose(f); return fail(FS3D_ERR_INVALID_ARG, why); }
+    if (h.format_version != FS3D_CKPT_VERSION || h.encoding != 1)
+        return fail(FS3D_ERR_INVALID_ARG, "unknown checkpoint format version / encoding");
+    if (h.schedule_version != FS3D_SCHEDULE_VERSION)
+        return fail(FS3D_ERR_INVALID_ARG, "checkpoint was written under another schedule version");
+    if (h.nx != w->desc.nx || h.ny != w->desc.ny || h.nz != w->desc.nz)
+        return fail(FS3D_ERR_INVALID_ARG, "checkpoint grid differs from the world's");
+    if (h.z_begin != zb || h.z_end != ze) return fail(FS3D_ERR_INVALID_ARG, "checkpoint holds other z-planes than this world");
+    if (h.payload_bytes != pb / 4 * (uint64_t)(ze - zb)) return fail(FS3D_ERR_INVALID_ARG, "checkpoint payload size is inconsistent");
     int rc = sync_all(w);
-    if (rc) { std::fclose(f); return rc; }
+    if (rc) return rc;
     // unpack into the BACK buffer, verify the digest there, then flip: a bad file leaves the world untouched
     const int back = w->cur ^ 1;
     const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / 4));
@@ -1322,27 +1332,19 @@ int fs3d_load(fs3d_world *w, const char *path) {
     uint64_t sum = 0;
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
-        uint32_t *d_packed = nullptr;
+        DevBuf packed;
         const uint32_t cp = std::min(planes_per_chunk, s.nzl);
-        cudaError_t e = cudaMalloc(&d_packed, (size_t)cp * (pb / 4));
-        if (e != cudaSuccess) { std::fclose(f); FS3D_CUDA(e); }
+        FS3D_CUDA(cudaMalloc(&packed.p, (size_t)cp * (pb / 4)));
         for (uint32_t z = 0; z < s.nzl; z += cp) {
             const uint32_t n = std::min(cp, s.nzl - z);
             const uint64_t n16 = pb * n / 16;
-            if (std::fread(host.data(), 1, n16 * 4, f) != n16 * 4) {
-                cudaFree(d_packed); std::fclose(f);
-                return fail(FS3D_ERR_IO, std::string(path) + " is truncated");
-            }
-            e = cudaMemcpyAsync(d_packed, host.data(), n16 * 4, cudaMemcpyHostToDevice, s.s_main);
-            if (e == cudaSuccess) {
-                unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(d_packed, n16, owned_ptr(w, s, back) + pb * z);
-                e = cudaGetLastError();
-            }
-            if (e == cudaSuccess) e = cudaStreamSynchronize(s.s_main);
-            if (e != cudaSuccess) { cudaFree(d_packed); std::fclose(f); FS3D_CUDA(e); }
+            if (std::fread(host.data(), 1, n16 * 4, in.f) != n16 * 4) return fail(FS3D_ERR_IO, std::string(path) + " is truncated");
+            FS3D_CUDA(cudaMemcpyAsync(packed.p, host.data(), n16 * 4, cudaMemcpyHostToDevice, s.s_main));
+            unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(packed.p, n16, owned_ptr(w, s, back) + pb * z);
+            FS3D_CUDA(cudaGetLastError());
             w->launches++;
+            FS3D_CUDA(cudaStreamSynchronize(s.s_main));      // `host` is reused by the next chunk
         }
-        cudaFree(d_packed);
         unsigned long long *d = s.d_scratch + 256, hsum = 0;
         FS3D_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), s.s_main));
         const uint64_t n16 = pb * s.nzl / 16;
@@ -1352,7 +1354,6 @@ int fs3d_load(fs3d_world *w, const char *path) {
         FS3D_CUDA(cudaStreamSynchronize(s.s_main));
         sum += hsum;
     }
-    std::fclose(f);
     if (sum != h.digest) return fail(FS3D_ERR_IO, std::string(path) + ": digest mismatch (corrupt checkpoint); world unchanged");
     w->cur = back;
     w->step = h.step;

@@ -14,10 +14,13 @@
 //  * The 32 bytes are bit-sliced into two 32-bit planes (bit0, bit1 of the material code) with
 //    voxel x at bit 8·(x&3) + ((x>>2)&7) — the transpose that makes byte<->plane conversion a
 //    few shifts/ands.  All rule evaluation is then 32 voxels per logic instruction.
-//  * XY blocks pair x with x±1: inside a word that is a byte permute (PRMT); across words the
-//    single edge bit comes from the neighbouring lane by warp shuffle.
+//  * XY blocks pair x with x±1: inside a word that is a byte permute (PRMT) — the two rows' left and
+//    right cells are gathered into separate words so each block is evaluated once; with odd
+//    x-offset the cells of the word-straddling block cross lanes by warp shuffle.
 //  * Loads for the next plane pair are issued before the current pair is evaluated
-//    (register double-buffering), so ~J·4 KiB per warp is always in flight.
+//    (register double-buffering), so ~J·4 KiB per warp is always in flight.  The loads are
+//    unconditional (clamped addresses): predicated ones made nvcc wait for the data right
+//    behind the LDG, which switched the double-buffering off.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -142,11 +145,10 @@ struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u3
 //
 // XW = warps per z-pair (1 or 2).  Rows wider than 64 words (nx > 2048) do not fit one warp's registers
 // at J = 4 (255 registers + spills, measured 40 % slower), so two adjacent warps of a CTA share the
-// z-pair instead: warp half h owns words [64h, 64h + 64).  The only thing they exchange is the one
-// edge word per row per XY sub-step that a single warp moves by shuffle.  It goes through one 32-bit
-// shared-memory mailbox per direction, tagged with a sequence number and polled by the consumer.
-// NOT a named barrier: BAR.SYNC also waits for the warp's outstanding global loads, which serialises
-// the register double-buffering (measured 4.15 ms instead of 2.75 ms per pass at 4096 x 4096 x 512).
+// z-pair instead: warp half h owns words [64h, 64h + 64).  The only thing they exchange is what a
+// single warp moves by shuffle at the word boundary in XY sub-steps with odd x-offset.  It goes through
+// 32-bit shared-memory mailboxes, tagged with a sequence number and polled by the consumer — no
+// barrier, so the two warps only ever wait for the one value they need.
 template <int J, int XW, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
 __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepParams p) {
     static_assert(NS == 1 || (NS == 2 && TODD == 0), "a fused pair of steps starts on an even step");
