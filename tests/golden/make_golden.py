@@ -35,3 +35,18 @@ for name, dims, scene, sseed, seed, cps in CASES:
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "digests.json"), "w") as f:
     json.dump(out, f, indent=1)
 print("wrote digests.json")
+
+# A golden STATE in the checkpoint format (include/fs3d.h): the MIXED_NOISE scene 64 x 32 x 16 (scene seed 6)
+# after 41 steps under seed 12 — an odd step index, so a resumed run must keep the schedule phase.
+from fallingsand3d_b200 import checkpoint  # noqa: E402
+
+g = oracle.generate(64, 32, 16, 4, 6)
+oracle.run(g, 12, 0, 41)
+here = os.path.dirname(os.path.abspath(__file__))
+checkpoint.write(os.path.join(here, "mixed_noise_64x32x16_t41.fs3d"), g, step=41, seed=12)
+oracle.run(g, 12, 41, 23)
+with open(os.path.join(here, "mixed_noise_64x32x16_t41.json"), "w") as f:
+    json.dump({"file": "mixed_noise_64x32x16_t41.fs3d", "dims": [64, 32, 16], "scene": 4, "scene_seed": 6, "seed": 12,
+               "step": 41, "resume_steps": 23, "digest_after_resume": hex(oracle.digest(g)),
+               "histogram": [int(v) for v in oracle.histogram(g)[:4]]}, f, indent=1)
+print("wrote mixed_noise_64x32x16_t41.fs3d")

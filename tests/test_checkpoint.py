@@ -57,6 +57,41 @@ def test_numpy_reader_rejects_damage(tmp_path):
         ck.write(p, np.full((1, 1, 32), 7, np.uint8))          # reserved material codes
 
 
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _golden():
+    import json
+    with open(os.path.join(GOLDEN, "mixed_noise_64x32x16_t41.json")) as f:
+        return json.load(f)
+
+
+def test_golden_state_file_is_what_the_oracle_produces(oracle):
+    # the committed checkpoint (tests/golden/make_golden.py) parses, verifies, and equals a fresh oracle run
+    meta = _golden()
+    h, g = ck.read(os.path.join(GOLDEN, meta["file"]))
+    nx, ny, nz = meta["dims"]
+    assert (h["nx"], h["ny"], h["nz"], h["step"], h["seed"]) == (nx, ny, nz, meta["step"], meta["seed"])
+    ref = oracle.generate(nx, ny, nz, meta["scene"], meta["scene_seed"])
+    oracle.run(ref, meta["seed"], 0, meta["step"])
+    assert np.array_equal(g, ref)
+    oracle.run(ref, meta["seed"], meta["step"], meta["resume_steps"])
+    assert hex(oracle.digest(ref)) == meta["digest_after_resume"]
+    assert [int(v) for v in oracle.histogram(ref)[:4]] == meta["histogram"]
+
+
+@pytest.mark.gpu
+def test_gpu_resumes_the_golden_state(fs3d):
+    meta = _golden()
+    nx, ny, nz = meta["dims"]
+    with fs3d.VoxelWorld(nx, ny, nz, seed=1) as w:
+        w.load(os.path.join(GOLDEN, meta["file"]))
+        assert w.step_index == meta["step"]
+        w.step(meta["resume_steps"])
+        assert hex(w.digest()) == meta["digest_after_resume"]
+        assert [int(v) for v in w.histogram()[:4]] == meta["histogram"]
+
+
 @pytest.mark.gpu
 def test_gpu_save_matches_numpy_reader_and_resume_is_bit_identical(tmp_path, fs3d, oracle):
     nx, ny, nz = 96, 40, 30
