@@ -309,7 +309,7 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
         const uint32_t units = (uint32_t)(blocks * warps_per_block / warps_per_pair(w->jidx));
         FS3D_CUDA(cudaMemsetAsync(s.d_nruns, 0, sizeof(uint32_t), s.s_main));
         skip_runs_kernel<<<(unsigned)((npg + 3) / 4), 128, 0, s.s_main>>>(
-            s.d_skip, s.nytiles, ZTILE_LOG2, YTILE_LOG2 - 1, s.nzl, L.lz_first, pb, pe, w->groups, p.nit, units,
+            s.d_skip, s.nytiles, ZTILE_LOG2, YTILE_LOG2 - 1, s.nzl, L.lz_first, pb, pe, w->groups, p.nit, (uint32_t)ns, units,
             s.d_tiles_run, s.d_runs, s.d_nruns);
         FS3D_CUDA(cudaGetLastError());
         w->launches++;

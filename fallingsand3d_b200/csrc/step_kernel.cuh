@@ -610,14 +610,16 @@ __global__ void skip_map_kernel(const uint32_t *last_active, uint8_t *skip, uint
     if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] = n;
 }
 
-// The live march segments of one launch, for the SKIP kernels: one WARP per pair group tests its
-// y-blocks 32 at a time (a block is static iff the tiles of both rows at y-tile b and b − 1 are quiet —
-// the test the march used to make per block), and lane 0 emits every maximal run of live blocks,
-// chopped into pieces of `chop` blocks so that every marching warp gets several runs.  Order in the
-// list is arbitrary: blocks write disjoint planes.
+// The live march segments of one launch, for the SKIP kernels.  One WARP per pair group looks at its
+// y-tiles 32 at a time (a tile is live unless skip_map_kernel proved it static for both rows) and lane 0
+// emits the runs: y-block b (BLK iterations) stores tile b's planes except its top LAG + 1, which the first
+// NS iterations of block b + 1 store.  So a maximal range of live tiles [Ta, Tb) needs iterations
+// [BLK·Ta, BLK·Tb + NS) — whole blocks plus a short tail, not the whole block Tb.  Ranges are chopped into
+// pieces of `chop` blocks so that every marching warp gets several runs.  Order in the list is arbitrary:
+// runs write disjoint planes (what a run stores into neighbouring static tiles is their unchanged content).
 __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t ztile_log2, uint32_t blk_log2,
                                  uint32_t nzl, uint32_t lz_first, uint32_t pair_begin, uint32_t pair_end,
-                                 uint32_t groups, uint32_t nit, uint32_t nw, const unsigned long long *stats,
+                                 uint32_t groups, uint32_t nit, uint32_t ns, uint32_t nw, const unsigned long long *stats,
                                  uint32_t *runs, uint32_t *nruns) {
     const uint32_t npairs = pair_end - pair_begin;
     const uint32_t npg = (npairs + groups - 1) / groups;
@@ -642,25 +644,24 @@ __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t
     };
     const uint32_t wpb = blockDim.x >> 5;
     for (uint32_t pg = blockIdx.x * wpb + (threadIdx.x >> 5); pg < npg; pg += gridDim.x * wpb) {
-        // live mask of blocks [base, base + 32): the four tile flags of a block are loaded side by side
+        // live mask of y-tiles [base, base + 32) for the rows of this pair group
         auto live_mask = [&](uint32_t base) -> uint32_t {
-            const uint32_t bi = base + lane;
+            const uint32_t yt = base + lane;
             bool act = false;
-            if (bi < nblk) {
+            if (yt < nblk) {
                 for (uint32_t g = 0; g < groups; ++g) {
                     const uint32_t pair = pair_begin + pg * groups + g;
                     if (pair >= pair_end) break;
                     const int32_t ozl = (int32_t)(lz_first + 2u * pair) - 1, ozr = ozl + 1;
-                    const bool q0 = quiet(ozl, bi), q1 = quiet(ozr, bi);
-                    const bool q2 = bi == 0u || quiet(ozl, bi - 1), q3 = bi == 0u || quiet(ozr, bi - 1);
-                    act = act || !(q0 & q1 & q2 & q3);
+                    const bool q0 = quiet(ozl, yt), q1 = quiet(ozr, yt);
+                    act = act || !(q0 & q1);
                 }
             }
             return __ballot_sync(0xFFFFFFFFu, act);
         };
-        // two sweeps over the blocks: count this pair group's runs, reserve them with ONE atomic, then write
-        // them in y order (so neighbouring warps of the march get neighbouring segments of one pair)
-        constexpr uint32_t CACHE = 4;              // masks of the first sweep are kept for up to 128 blocks
+        // two sweeps: count this pair group's runs, reserve them with ONE atomic, then write them in y order
+        // (so neighbouring warps of the march get neighbouring segments of one pair)
+        constexpr uint32_t CACHE = 4;              // masks of the first sweep are kept for up to 128 tiles
         uint32_t cache[CACHE];
         uint32_t count = 0, at = 0;
         for (int sweep = 0; sweep < 2; ++sweep) {
@@ -672,12 +673,13 @@ __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t
                 if (lane == 0) {
                     for (uint32_t k = 0; k < 32u && base + k <= nblk; ++k) {
                         const uint32_t b = base + k;
-                        const bool a = (mask >> k) & 1u;
+                        const bool a = (mask >> k) & 1u;           // tile b live (never for b >= nblk)
                         if (start >= 0 && (!a || b - (uint32_t)start == chop)) {
                             if (sweep == 0) {
                                 ++count;
                             } else {
-                                const uint32_t e = b << blk_log2;
+                                uint32_t e = b << blk_log2;
+                                if (!a) e += ns;                     // the range ends here: tail that stores the last tile's top planes
                                 runs[3u * at] = pg; runs[3u * at + 1u] = (uint32_t)start << blk_log2; runs[3u * at + 2u] = e < nit ? e : nit;
                                 ++at;
                             }
