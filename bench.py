@@ -135,6 +135,10 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm runs alone on rank 0 and is meant to use every
+    # host thread it can, so undo that before libgomp is loaded (the oracle library is the first OpenMP user here)
+    if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ.pop("OMP_NUM_THREADS", None)
     from oracle import oracle
     n = args.size
     nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))
