@@ -97,6 +97,7 @@ struct fs3d_world {
     int pass_ns = 1;             // steps fused in the current external pass
     bool p2p = false;            // slab world with IPC-attached neighbours: fused halo push, fs3d_step allowed
     unsigned long long wait_target = 0;   // iterations each neighbour has delivered before the next pass
+    bool ghosts_stale = false;   // slab world after fs3d_slab_step_host: fs3d_slab_push_halos must run before fs3d_step
 };
 
 namespace fs3d {
@@ -685,6 +686,8 @@ int fs3d_step(fs3d_world *w, uint32_t n_steps) {
     if (w->external && w->desc.nz != w->slabs[0].nzl && !w->p2p)
         return fail(FS3D_ERR_UNSUPPORTED, "slab worlds step through fs3d_slab_step_* with a caller-driven halo exchange, "
                                           "or through fs3d_step after fs3d_slab_ipc_attach");
+    if (w->ghosts_stale)
+        return fail(FS3D_ERR_UNSUPPORTED, "after fs3d_slab_step_host call fs3d_slab_push_halos on every rank (and barrier) before fs3d_step");
     uint32_t left = n_steps;
     while (left > 0) {
         // steps 2k and 2k + 1 share the z-pairing and x-offset, so they fuse into one pass
@@ -1024,12 +1027,9 @@ int fs3d_slab_pass_steps(fs3d_world *w, uint32_t n_steps) {
 }
 
 // ---- out-of-core / end-to-end step: host grid in, host grid out, copies overlapped with compute ----
-int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
-    if (!w || !host_in || !host_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
-    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host advances 1 or 2 steps per call");
-    if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
-    if (w->slabs.size() != 1 || (w->external && w->desc.nz != w->slabs[0].nzl))
-        return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host needs a single-slab world that holds the whole grid");
+// Streams the planes a single-slab world holds through the GPU; the ghost planes of the front buffer must
+// already be right (STONE at the global boundary, the neighbours' edge planes for a rank's slab).
+static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
     int rc = sync_all(w);
     if (rc) return rc;
     Slab &s = w->slabs[0];
@@ -1089,6 +1089,48 @@ int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uin
     if (bad) return fail(FS3D_ERR_BAD_MATERIAL, "host grid contains material codes 4-255 (reserved); the world now holds "
                                                 "undefined cells - upload or generate before stepping again");
     return FS3D_OK;
+}
+
+int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
+    if (!w || !host_in || !host_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host advances 1 or 2 steps per call");
+    if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
+    if (w->slabs.size() != 1 || (w->external && w->desc.nz != w->slabs[0].nzl))
+        return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host needs a single-slab world that holds the whole grid "
+                                          "(ranks use fs3d_slab_step_host_begin + fs3d_slab_step_host)");
+    return step_host_stream(w, host_in, host_out, n_steps);
+}
+
+// One rank's share of the same end-to-end step.  _begin uploads the slab's two edge planes and stores them into the
+// neighbours' ghost planes over peer memory; after a barrier, fs3d_slab_step_host streams the slab through.
+int fs3d_slab_step_host_begin(fs3d_world *w, const uint8_t *host_in) {
+    if (!w || !host_in) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (!w->external || !w->p2p) return fail(FS3D_ERR_UNSUPPORTED, "needs a slab world with attached neighbours (fs3d_slab_ipc_attach)");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    const size_t pb = plane_bytes(w);
+    uint8_t *src = s.buf[w->cur];
+    FS3D_CUDA(cudaMemcpyAsync(src + pb, host_in, pb, cudaMemcpyHostToDevice, s.s_main));
+    if (s.nzl > 1)
+        FS3D_CUDA(cudaMemcpyAsync(src + pb * (size_t)s.nzl, host_in + pb * (size_t)(s.nzl - 1), pb, cudaMemcpyHostToDevice, s.s_main));
+    if (s.peer_lo.valid)
+        FS3D_CUDA(cudaMemcpyAsync(s.peer_lo.buf[w->cur] + pb * ((size_t)s.peer_lo.nzl + 1), src + pb, pb, cudaMemcpyDefault, s.s_main));
+    if (s.peer_hi.valid)
+        FS3D_CUDA(cudaMemcpyAsync(s.peer_hi.buf[w->cur], src + pb * (size_t)s.nzl, pb, cudaMemcpyDefault, s.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    return FS3D_OK;
+}
+
+int fs3d_slab_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
+    if (!w || !host_in || !host_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_slab_step_host advances 1 or 2 steps per call");
+    if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
+    if (!w->external || !w->p2p) return fail(FS3D_ERR_UNSUPPORTED, "needs a slab world with attached neighbours (fs3d_slab_ipc_attach)");
+    int rc = step_host_stream(w, host_in, host_out, n_steps);
+    w->ghosts_stale = true;     // the new front buffer's ghost planes were not exchanged
+    return rc;
 }
 
 // ---- fused halo push between ranks: CUDA IPC plumbing ---------------------------------------------
@@ -1158,6 +1200,7 @@ int fs3d_slab_push_halos(fs3d_world *w) {
     if (s.peer_hi.valid)
         FS3D_CUDA(cudaMemcpyAsync(s.peer_hi.buf[w->cur], s.buf[w->cur] + pb * (size_t)s.nzl, pb, cudaMemcpyDefault, s.s_main));
     FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    w->ghosts_stale = false;
     return FS3D_OK;
 }
 

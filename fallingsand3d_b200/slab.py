@@ -218,7 +218,28 @@ class SlabWorld:
         if self.world_size > 1:
             self.refresh_halos()
 
+    def step_host(self, host_in, host_out=None, n=1):
+        """End-to-end step of a host-resident slab (pinned memory recommended): every rank streams its planes
+        through its GPU with overlapped copies; only the two edge planes are exchanged first (peer memory)."""
+        if not self.p2p:
+            self.upload(host_in)
+            self.step(n)
+            out = host_in if host_out is None else host_out
+            out[...] = self.download()
+            return out
+        w = self.engine.world
+        w.slab_step_host_begin(host_in)
+        dist.barrier(group=self.group)          # every ghost plane holds its neighbour's edge plane
+        out = w.slab_step_host(host_in, host_out, n)
+        dist.barrier(group=self.group)          # ghost planes may be overwritten by the next call
+        self.step_index += int(n)
+        self._halos_stale = True
+        return out
+
     def step(self, n=1):
+        if getattr(self, "_halos_stale", False):
+            self._halos_stale = False
+            self.refresh_halos()
         if self.p2p:
             self.engine.world.step(int(n))      # the library loops; halos move inside the kernels
             self.step_index += int(n)

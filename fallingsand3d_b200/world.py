@@ -243,6 +243,19 @@ class VoxelWorld:
         hi = C.create_string_buffer(upper_blob, self.IPC_BLOB_BYTES) if upper_blob is not None else None
         _check(self._lib.fs3d_slab_ipc_attach(self._h, lo, hi))
 
+    def slab_step_host_begin(self, grid_in):
+        assert grid_in.dtype == np.uint8 and grid_in.flags.c_contiguous and grid_in.shape == self.shape
+        _check(self._lib.fs3d_slab_step_host_begin(self._h, grid_in.ctypes.data_as(C.c_void_p)))
+
+    def slab_step_host(self, grid_in, grid_out=None, n=1):
+        if grid_out is None:
+            grid_out = grid_in
+        for g in (grid_in, grid_out):
+            assert g.dtype == np.uint8 and g.flags.c_contiguous and g.shape == self.shape
+        _check(self._lib.fs3d_slab_step_host(self._h, grid_in.ctypes.data_as(C.c_void_p),
+                                             grid_out.ctypes.data_as(C.c_void_p), int(n)))
+        return grid_out
+
     def slab_push_halos(self):
         _check(self._lib.fs3d_slab_push_halos(self._h))
 

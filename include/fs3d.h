@@ -144,6 +144,17 @@ int  fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kerne
  * (use pinned host memory).  host_in may equal host_out.  Single-slab worlds only. */
 int  fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps);
 
+/* The same for one rank's slab of a fused-halo-push world (after fs3d_slab_ipc_attach):
+ *   fs3d_slab_step_host_begin(w, host_in)   uploads the slab's two edge planes and stores them into the
+ *                                           neighbours' ghost planes over peer memory
+ *   -- barrier across ranks --
+ *   fs3d_slab_step_host(w, host_in, host_out, n)   streams the slab through like fs3d_step_host
+ *   -- barrier across ranks before the next _begin --
+ * Afterwards the device holds the stepped slab but not its neighbours' new edge planes: call
+ * fs3d_slab_push_halos on every rank (and barrier) before going back to fs3d_step. */
+int  fs3d_slab_step_host_begin(fs3d_world *w, const uint8_t *host_in);
+int  fs3d_slab_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps);
+
 /* ---- reductions (over the planes this world holds; sum across ranks yourself) ---- */
 int  fs3d_histogram(fs3d_world *w, uint64_t counts[256]);
 int  fs3d_digest(fs3d_world *w, uint64_t *out);
