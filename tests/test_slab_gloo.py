@@ -57,6 +57,34 @@ def test_slab_world_matches_whole_grid_oracle(oracle, world_size, dims, chunk):
     assert [o[4] for o in out] == slab_bounds(nz, world_size)
 
 
+def _step_host_worker(rank, world_size, dims, seed):
+    from fallingsand3d_b200.slab import SlabWorld
+    from oracle import oracle
+    nx, ny, nz = dims
+    sw = SlabWorld(nx, ny, nz, seed=seed, engine_factory=OracleSlabEngine)
+    full = oracle.generate(nx, ny, nz, 4, 2)
+    host = full[sw.z_begin:sw.z_end].copy()      # a copy: the slice itself is contiguous and would alias `full`
+    out = np.empty_like(host)
+    t = 0
+    for n in (2, 1, 1, 2):                       # host slab in, stepped host slab out, every call
+        sw.step_host(host, out, n)
+        oracle.run(full, seed, t, n)
+        t += n
+        assert np.array_equal(out, full[sw.z_begin:sw.z_end]), f"rank {rank} after step {t}"
+        host, out = out, host
+    sw.step(3)                                   # and ordinary stepping continues from the stepped state
+    oracle.run(full, seed, t, 3)
+    assert np.array_equal(sw.download(), full[sw.z_begin:sw.z_end])
+    return sw.step_index
+
+
+@pytest.mark.parametrize("world_size,dims", [(2, (32, 10, 9)), (3, (64, 8, 12))])
+def test_step_host_on_host_resident_slabs(world_size, dims):
+    # the transport-independent fallback of SlabWorld.step_host (upload + step + download per rank); the GPU
+    # ranks stream their slabs instead (tests/run_slab_ranks.py)
+    assert run_ranks(world_size, _step_host_worker, dims, 17) == [9] * world_size
+
+
 def test_u64_allreduce_wraps_like_the_digest():
     out = run_ranks(2, _wrap_worker)
     assert out[0] == out[1] == [(2 ** 64 - 5 + 2 ** 63 + 11) % 2 ** 64, 7]
