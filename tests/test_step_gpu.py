@@ -204,6 +204,10 @@ def test_step_host_streams_a_host_grid(fs3d, oracle, dims):
         with pytest.raises(fs3d.Fs3dError) as ei:
             w.step_host(bad, out, 1)
         assert ei.value.code == -3
+        for call in (lambda: w.slab_step_host_begin(host), lambda: w.slab_step_host(host, out, 1)):
+            with pytest.raises(fs3d.Fs3dError) as ei:      # the per-rank variant needs attached neighbours
+                call()
+            assert ei.value.code == -7
 
 
 def test_paint_sphere_brush(fs3d, oracle):
