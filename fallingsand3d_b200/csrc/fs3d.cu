@@ -52,6 +52,8 @@ struct Slab {
     unsigned long long *d_scratch = nullptr;   // 256 + 1 u64 + 1 u32 flag
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
     float *d_palette = nullptr;
+    float *d_thr = nullptr;          // 256 sRGB thresholds (ray-march of this slab into a frame slot)
+    bool palette_current = false;    // d_palette holds the world's palette
     int num_sms = 0;
     int blocks_per_sm[2][2][2][2][2] = {};   // [PUSH][NS-1][SKIP][OX][TODD] for this world's J
     // fused halo push (one process per GPU, CUDA IPC): my arrival counters and the neighbours' memory
@@ -91,7 +93,6 @@ struct fs3d_world {
     uint64_t launches = 0;       // kernels launched since creation
     int jidx = 0;                // kernel shape, see step_threads()
     uint32_t lpr = 32, groups = 1;
-    bool palette_dirty = true;
     float palette[256 * 4];
     int edges_phase = 0;         // external stepping protocol state
     int pass_ns = 1;             // steps fused in the current external pass
@@ -159,6 +160,7 @@ static int init_slab(fs3d_world *w, Slab &s) {
     FS3D_CUDA(cudaEventCreate(&s.ev_t1));
     FS3D_CUDA(cudaMalloc(&s.d_scratch, 260 * sizeof(unsigned long long)));
     FS3D_CUDA(cudaMalloc(&s.d_palette, 256 * 4 * sizeof(float)));
+    FS3D_CUDA(cudaMalloc(&s.d_thr, 256 * sizeof(float)));
     FS3D_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, s.device));
     for (int pu = 0; pu < 2; ++pu)
         for (int ns = 1; ns <= 2; ++ns)
@@ -213,6 +215,7 @@ static void free_slab(Slab &s) {
     if (s.d_scratch) cudaFree(s.d_scratch);
     if (s.d_img) cudaFree(s.d_img);
     if (s.d_palette) cudaFree(s.d_palette);
+    if (s.d_thr) cudaFree(s.d_thr);
     if (s.d_skip) cudaFree(s.d_skip);
     if (s.d_last_active) cudaFree(s.d_last_active);
     if (s.d_tiles_run) cudaFree(s.d_tiles_run);
@@ -479,37 +482,7 @@ static unsigned grid_for(uint64_t n, const Slab &s) {
 }
 
 // ---- raymarch host side ----------------------------------------------------------------------------
-int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode,
-                   uint8_t *host_rgba8, float *host_depth, unsigned long long *frame_slot) {
-    if ((int)w->slabs.size() > RM_MAX_SLABS) return fail(FS3D_ERR_UNSUPPORTED, "too many slabs for raymarch");
-    if ((mode & 15u) > FS3D_RM_VOXELS) return fail(FS3D_ERR_INVALID_ARG, "unknown raymarch mode");
-    Slab &s0 = w->slabs[0];
-    FS3D_CUDA(cudaSetDevice(s0.device));
-    // device 0 of the world reads every slab (peer access over NVLink for in-process multi-GPU)
-    for (size_t i = 1; i < w->slabs.size(); ++i) {
-        if (w->slabs[i].device == s0.device) continue;
-        int can = 0;
-        FS3D_CUDA(cudaDeviceCanAccessPeer(&can, s0.device, w->slabs[i].device));
-        if (!can) return fail(FS3D_ERR_UNSUPPORTED, "raymarch needs peer access from the first slab's device");
-        cudaError_t e = cudaDeviceEnablePeerAccess(w->slabs[i].device, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FS3D_CUDA(e);
-        cudaGetLastError();
-    }
-    const size_t npix = (size_t)width * height;
-    const size_t need = npix * 4 + npix * sizeof(float) + 256 * sizeof(float);
-    if (s0.img_bytes < need) {
-        if (s0.d_img) cudaFree(s0.d_img);
-        s0.d_img = nullptr; s0.img_bytes = 0;
-        FS3D_CUDA(cudaMalloc(&s0.d_img, need));
-        s0.img_bytes = need;
-    }
-    float *d_depth = reinterpret_cast<float *>(s0.d_img + npix * 4);
-    float *d_thr = d_depth + npix;
-    if (w->palette_dirty) {
-        FS3D_CUDA(cudaMemcpyAsync(s0.d_palette, w->palette, sizeof(w->palette), cudaMemcpyHostToDevice, s0.s_main));
-        w->palette_dirty = false;
-    }
-    RMParams p{};
+static void rm_camera(const fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode, RMParams &p) {
     p.ox = cam->pos[0]; p.oy = cam->pos[1]; p.oz = cam->pos[2];
     const double yaw = (double)cam->yaw_deg * 3.14159265358979323846 / 180.0;
     p.cs = cam->yaw_deg == 0.0f ? 1.0f : (float)std::cos(yaw);
@@ -520,6 +493,123 @@ int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32
     const uint32_t nmax = std::max(p.nx, std::max(p.ny, p.nz));
     p.h = 1.0f / (float)nmax;
     p.ex = (float)p.nx * p.h * 0.5f; p.ey = (float)p.ny * p.h * 0.5f; p.ez = (float)p.nz * p.h * 0.5f;
+}
+
+// (re)allocates the frame a world owns: n_slots x (width x height) 64-bit words + the resolved image
+static int ensure_frame(Slab &s, uint32_t width, uint32_t height, uint32_t n_slots) {
+    if (s.frame.base && s.frame.owner && s.frame.width == width && s.frame.height == height && s.frame.nslots == n_slots)
+        return FS3D_OK;
+    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else cudaIpcCloseMemHandle(s.frame.base); }
+    if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
+    s.frame = Slab::Frame();
+    const size_t npix = (size_t)width * height;
+    FS3D_CUDA(cudaMalloc(&s.frame.base, npix * n_slots * sizeof(unsigned long long)));
+    s.frame.owner = true;
+    FS3D_CUDA(cudaMalloc(&s.frame.d_rgba, npix * (sizeof(uint32_t) + sizeof(float))));   // image, then depth
+    FS3D_CUDA(cudaMemset(s.frame.base, 0xFF, npix * n_slots * sizeof(unsigned long long)));   // every slot: all misses
+    s.frame.width = width; s.frame.height = height; s.frame.nslots = n_slots; s.frame.slot = 0;
+    return FS3D_OK;
+}
+
+// march one slab of the world on its own device into `frame_slot` (asynchronous on the slab's stream)
+static int raymarch_slab_to_frame(fs3d_world *w, Slab &s, const fs3d_camera *cam, uint32_t width, uint32_t height,
+                                  uint32_t mode, unsigned long long *frame_slot) {
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if (!s.palette_current) {
+        FS3D_CUDA(cudaMemcpyAsync(s.d_palette, w->palette, sizeof(w->palette), cudaMemcpyHostToDevice, s.s_main));
+        s.palette_current = true;
+    }
+    RMParams p{};
+    rm_camera(w, cam, width, height, mode, p);
+    p.nslabs = 1;
+    p.slab_ptr[0] = owned_ptr(w, s, w->cur);
+    p.slab_z0[0] = s.z0; p.slab_z1[0] = s.z0 + s.nzl;
+    p.palette = s.d_palette;
+    if (mode & FS3D_RM_SRGB) {
+        float thr[256];
+        srgb_thresholds(thr);
+        thr[255] = INFINITY;
+        FS3D_CUDA(cudaMemcpyAsync(s.d_thr, thr, sizeof(thr), cudaMemcpyHostToDevice, s.s_main));
+        p.srgb_thr = s.d_thr;
+    }
+    p.frame = frame_slot;
+    dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
+    raymarch_kernel<<<grd, blk, 0, s.s_main>>>(p);
+    FS3D_CUDA(cudaGetLastError());
+    w->launches++;
+    return FS3D_OK;
+}
+
+int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode,
+                   uint8_t *host_rgba8, float *host_depth, unsigned long long *frame_slot) {
+    if ((mode & 15u) > FS3D_RM_VOXELS) return fail(FS3D_ERR_INVALID_ARG, "unknown raymarch mode");
+    Slab &s0 = w->slabs[0];
+    if (frame_slot) return raymarch_slab_to_frame(w, s0, cam, width, height, mode, frame_slot);   // a rank's slab -> the compositor
+
+    const size_t npix = (size_t)width * height;
+    if (w->slabs.size() > 1 && w->p2p && !w->external) {
+        // One slab per device with peer access: every device marches its OWN slab and stores (t, rgba) straight
+        // into its slot of a frame on the first device; that device keeps the nearest hit per pixel.  Nothing
+        // but the finished pixels crosses NVLink.
+        bool ok = true;
+        for (size_t i = 1; i < w->slabs.size() && ok; ++i) {
+            int can = 0;
+            FS3D_CUDA(cudaDeviceCanAccessPeer(&can, w->slabs[i].device, s0.device));
+            if (!can) { ok = false; break; }
+            FS3D_CUDA(cudaSetDevice(w->slabs[i].device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(s0.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+            cudaGetLastError();
+        }
+        if (ok) {
+            FS3D_CUDA(cudaSetDevice(s0.device));
+            int rc = ensure_frame(s0, width, height, (uint32_t)w->slabs.size());
+            if (rc) return rc;
+            for (size_t i = 0; i < w->slabs.size(); ++i) {
+                rc = raymarch_slab_to_frame(w, w->slabs[i], cam, width, height, mode, s0.frame.base + npix * i);
+                if (rc) return rc;
+            }
+            rc = sync_all(w);
+            if (rc) return rc;
+            FS3D_CUDA(cudaSetDevice(s0.device));
+            float *d_depth = reinterpret_cast<float *>(s0.frame.d_rgba + npix);
+            frame_resolve_kernel<<<grid_for(npix, s0), 256, 0, s0.s_main>>>(s0.frame.base, s0.frame.nslots, npix, s0.frame.d_rgba,
+                                                                            host_depth ? d_depth : nullptr);
+            FS3D_CUDA(cudaGetLastError());
+            w->launches++;
+            FS3D_CUDA(cudaMemcpyAsync(host_rgba8, s0.frame.d_rgba, npix * 4, cudaMemcpyDeviceToHost, s0.s_main));
+            if (host_depth) FS3D_CUDA(cudaMemcpyAsync(host_depth, d_depth, npix * sizeof(float), cudaMemcpyDeviceToHost, s0.s_main));
+            FS3D_CUDA(cudaStreamSynchronize(s0.s_main));
+            return FS3D_OK;
+        }
+    }
+
+    // one device marches every slab (slabs on the same device, or reached through peer loads)
+    if ((int)w->slabs.size() > RM_MAX_SLABS) return fail(FS3D_ERR_UNSUPPORTED, "too many slabs for raymarch");
+    FS3D_CUDA(cudaSetDevice(s0.device));
+    for (size_t i = 1; i < w->slabs.size(); ++i) {
+        if (w->slabs[i].device == s0.device) continue;
+        int can = 0;
+        FS3D_CUDA(cudaDeviceCanAccessPeer(&can, s0.device, w->slabs[i].device));
+        if (!can) return fail(FS3D_ERR_UNSUPPORTED, "raymarch needs peer access from the first slab's device");
+        cudaError_t e = cudaDeviceEnablePeerAccess(w->slabs[i].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FS3D_CUDA(e);
+        cudaGetLastError();
+    }
+    const size_t need = npix * 4 + npix * sizeof(float);
+    if (s0.img_bytes < need) {
+        if (s0.d_img) cudaFree(s0.d_img);
+        s0.d_img = nullptr; s0.img_bytes = 0;
+        FS3D_CUDA(cudaMalloc(&s0.d_img, need));
+        s0.img_bytes = need;
+    }
+    float *d_depth = reinterpret_cast<float *>(s0.d_img + npix * 4);
+    if (!s0.palette_current) {
+        FS3D_CUDA(cudaMemcpyAsync(s0.d_palette, w->palette, sizeof(w->palette), cudaMemcpyHostToDevice, s0.s_main));
+        s0.palette_current = true;
+    }
+    RMParams p{};
+    rm_camera(w, cam, width, height, mode, p);
     p.nslabs = (int)w->slabs.size();
     for (int i = 0; i < p.nslabs; ++i) {
         p.slab_ptr[i] = owned_ptr(w, w->slabs[i], w->cur);
@@ -532,17 +622,16 @@ int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32
         float thr[256];
         srgb_thresholds(thr);
         thr[255] = INFINITY;
-        FS3D_CUDA(cudaMemcpyAsync(d_thr, thr, sizeof(thr), cudaMemcpyHostToDevice, s0.s_main));
-        p.srgb_thr = d_thr;
+        FS3D_CUDA(cudaMemcpyAsync(s0.d_thr, thr, sizeof(thr), cudaMemcpyHostToDevice, s0.s_main));
+        p.srgb_thr = s0.d_thr;
     }
     p.img = s0.d_img;
     p.depth = d_depth;
-    p.frame = frame_slot;
+    p.frame = nullptr;
     dim3 blk(16, 16), grd((width + 15) / 16, (height + 15) / 16);
     raymarch_kernel<<<grd, blk, 0, s0.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
-    if (frame_slot) return FS3D_OK;   // asynchronous: the pixels went straight into the compositor's frame
     FS3D_CUDA(cudaMemcpyAsync(host_rgba8, s0.d_img, npix * 4, cudaMemcpyDeviceToHost, s0.s_main));
     if (host_depth) FS3D_CUDA(cudaMemcpyAsync(host_depth, d_depth, npix * sizeof(float), cudaMemcpyDeviceToHost, s0.s_main));
     FS3D_CUDA(cudaStreamSynchronize(s0.s_main));
@@ -944,7 +1033,7 @@ int fs3d_volume_view(fs3d_world *w, int32_t slab, fs3d_view *out) {
 int fs3d_set_palette(fs3d_world *w, const float *rgba256x4) {
     if (!w || !rgba256x4) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
     std::memcpy(w->palette, rgba256x4, sizeof(w->palette));
-    w->palette_dirty = true;
+    for (auto &s : w->slabs) s.palette_current = false;
     return FS3D_OK;
 }
 
@@ -1219,17 +1308,9 @@ int fs3d_frame_export(fs3d_world *w, uint32_t width, uint32_t height, uint32_t n
     FS3D_CUDA(cudaSetDevice(s.device));
     int rc = sync_all(w);
     if (rc) return rc;
-    if (s.frame.base) {
-        if (s.frame.owner) cudaFree(s.frame.base); else cudaIpcCloseMemHandle(s.frame.base);
-        if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
-        s.frame = Slab::Frame();
-    }
-    const size_t npix = (size_t)width * height;
-    FS3D_CUDA(cudaMalloc(&s.frame.base, npix * n_slots * sizeof(unsigned long long)));
-    s.frame.owner = true;
-    FS3D_CUDA(cudaMalloc(&s.frame.d_rgba, npix * sizeof(uint32_t)));
-    FS3D_CUDA(cudaMemset(s.frame.base, 0xFF, npix * n_slots * sizeof(unsigned long long)));   // every slot: all misses
-    s.frame.width = width; s.frame.height = height; s.frame.nslots = n_slots; s.frame.slot = 0;
+    s.frame.width = 0;                      // force a fresh (cleared) frame
+    rc = ensure_frame(s, width, height, n_slots);
+    if (rc) return rc;
     FrameBlob b{};
     b.magic = 0xF53DF4A3u; b.width = width; b.height = height; b.nslots = n_slots;
     FS3D_CUDA(cudaIpcGetMemHandle(&b.mem, s.frame.base));
@@ -1272,7 +1353,7 @@ int fs3d_frame_resolve(fs3d_world *w, uint8_t *host_rgba8) {
     if (!s.frame.base || !s.frame.owner) return fail(FS3D_ERR_UNSUPPORTED, "only the rank that called fs3d_frame_export resolves");
     FS3D_CUDA(cudaSetDevice(s.device));
     const size_t npix = (size_t)s.frame.width * s.frame.height;
-    frame_resolve_kernel<<<grid_for(npix, s), 256, 0, s.s_main>>>(s.frame.base, s.frame.nslots, npix, s.frame.d_rgba);
+    frame_resolve_kernel<<<grid_for(npix, s), 256, 0, s.s_main>>>(s.frame.base, s.frame.nslots, npix, s.frame.d_rgba, nullptr);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
     FS3D_CUDA(cudaMemcpyAsync(host_rgba8, s.frame.d_rgba, npix * 4, cudaMemcpyDeviceToHost, s.s_main));

@@ -223,7 +223,8 @@ __global__ void raymarch_kernel(const RMParams p) {
 
 // Compositor: per pixel the slot with the smallest hit parameter wins (a miss is +inf and black,
 // exactly what every rank wrote for it, so the minimum is right for misses too).
-__global__ void frame_resolve_kernel(const unsigned long long *frame, uint32_t nslots, size_t npix, uint32_t *rgba) {
+__global__ void frame_resolve_kernel(const unsigned long long *frame, uint32_t nslots, size_t npix, uint32_t *rgba,
+                                     float *depth /* may be nullptr */) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         unsigned long long best = frame[i];
         for (uint32_t s = 1; s < nslots; ++s) {
@@ -231,6 +232,7 @@ __global__ void frame_resolve_kernel(const unsigned long long *frame, uint32_t n
             best = v < best ? v : best;
         }
         rgba[i] = (uint32_t)best;
+        if (depth) depth[i] = __uint_as_float((uint32_t)(best >> 32));
     }
 }
 
