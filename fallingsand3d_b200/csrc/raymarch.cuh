@@ -53,14 +53,17 @@ __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, fl
     return fadd(fadd(fmul(ax, bx), fmul(ay, by)), fmul(az, bz));
 }
 __device__ __forceinline__ float len3(float x, float y, float z) { return fsqrt(dot3(x, y, z, x, y, z)); }
+// GLSL normalize evaluated the way the reference's vendored glm does (v * (1 / sqrt(dot(v, v)))): with this form the
+// oracle — and therefore this kernel — is bit-identical to fs_raymarch.frag compiled against that glm (oracle/_ref)
+__device__ __forceinline__ float inv_len3(float x, float y, float z) { return fdiv(1.0f, fsqrt(dot3(x, y, z, x, y, z))); }
 
 __device__ __forceinline__ float sphere_sdf(float x, float y, float z) { return fsub(len3(x, y, z), 0.5f); }
 
 __device__ __forceinline__ float diffuse_at(float px, float py, float pz, float nx, float ny, float nz) {
     // direction_to_light = normalize(p - light_pos), light_pos = (2, 5, 3)   [fs_raymarch.frag:49-53]
     float lx = fsub(px, 2.0f), ly = fsub(py, 5.0f), lz = fsub(pz, 3.0f);
-    float ll = len3(lx, ly, lz);
-    lx = fdiv(lx, ll); ly = fdiv(ly, ll); lz = fdiv(lz, ll);
+    float il = inv_len3(lx, ly, lz);
+    lx = fmul(lx, il); ly = fmul(ly, il); lz = fmul(lz, il);
     float d = dot3(nx, ny, nz, lx, ly, lz);
     return d > 0.05f ? d : 0.05f;
 }
@@ -94,8 +97,8 @@ __global__ void raymarch_kernel(const RMParams p) {
     float v = fdiv(fadd((float)py, 0.5f), (float)p.H);
     float qx = fsub(fmul(u, 2.0f), 1.0f);
     float qy = fmul(fsub(fmul(v, 2.0f), 1.0f), fdiv(1.0f, p.aspect));
-    float ql = len3(qx, qy, 1.0f);
-    float dx = fdiv(qx, ql), dy = fdiv(qy, ql), dz = fdiv(1.0f, ql);
+    float iq = inv_len3(qx, qy, 1.0f);
+    float dx = fmul(qx, iq), dy = fmul(qy, iq), dz = fmul(1.0f, iq);
     // optional yaw about y (camRot.y, renderer.cpp:460-467); identity when cs = 1, sn = 0
     {
         float rx = fadd(fmul(p.cs, dx), fmul(p.sn, dz));
@@ -115,8 +118,8 @@ __global__ void raymarch_kernel(const RMParams p) {
                 float gx = fsub(sphere_sdf(fadd(cx, e), cy, cz), sphere_sdf(fsub(cx, e), cy, cz));
                 float gy = fsub(sphere_sdf(cx, fadd(cy, e), cz), sphere_sdf(cx, fsub(cy, e), cz));
                 float gz = fsub(sphere_sdf(cx, cy, fadd(cz, e)), sphere_sdf(cx, cy, fsub(cz, e)));
-                float gl = len3(gx, gy, gz);
-                gx = fdiv(gx, gl); gy = fdiv(gy, gl); gz = fdiv(gz, gl);
+                float ig = inv_len3(gx, gy, gz);
+                gx = fmul(gx, ig); gy = fmul(gy, ig); gz = fmul(gz, ig);
                 r = diffuse_at(cx, cy, cz, gx, gy, gz);   // vec3(1,0,0) * diffuse
                 depth = t;
                 break;

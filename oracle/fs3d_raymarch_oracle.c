@@ -9,8 +9,9 @@
  *   /root/reference/shaders/fs_raymarch.frag:38-65  ray_march (64 iterations, 0.001 hit, 1000 far, light (2,5,3))
  *   /root/reference/shaders/fs_raymarch.frag:67-81  main (uv*2-1, y /= aspect, normalize(vec3(uv,1)))
  *   /root/reference/src/engine/rendering/renderer.cpp:1253-1267  quad UVs => u = 1-(px+.5)/W, v = (py+.5)/H
- * Pinned against the known-answer pixels SURVEY.md §8c derived from that shader
- * (tests/test_raymarch_oracle.py).  The voxel-DDA mode has no reference counterpart
+ * Pinned: bit-identical (hit mask, linear float colour, 8-bit image) to the reference shader source itself compiled
+ * against the reference's vendored glm (oracle/_ref via `make ref`; golden frames tests/golden/fs_raymarch_ref_frames.npz),
+ * and to the known-answer pixels of SURVEY.md §8c (tests/test_raymarch_oracle.py).  The voxel-DDA mode has no reference counterpart
  * (fs_raymarch takes no volume input — materials.cpp:520-521 creates it with zero bindings).
  *
  * Compile with -ffp-contract=off: every operation below is a separately rounded float op in the
@@ -24,12 +25,16 @@ static float dot3(float ax, float ay, float az, float bx, float by, float bz) {
     float s = ax * bx; float t = ay * by; s = s + t; t = az * bz; return s + t;
 }
 static float len3(float x, float y, float z) { return sqrtf(dot3(x, y, z, x, y, z)); }
+/* GLSL normalize as the reference's vendored glm 0.9.9.7 evaluates it (detail/func_geometric.inl: v * inversesqrt(dot(v, v)),
+ * inversesqrt(x) = 1 / sqrt(x)); with this form the frame is bit-identical to fs_raymarch.frag compiled against that glm
+ * (oracle/_ref, tests/test_raymarch_oracle.py). */
+static float inv_len3(float x, float y, float z) { return 1.0f / sqrtf(dot3(x, y, z, x, y, z)); }
 static float sphere_sdf(float x, float y, float z) { return len3(x, y, z) - 0.5f; }
 
 static float diffuse_at(float px, float py, float pz, float nx, float ny, float nz) {
     float lx = px - 2.0f, ly = py - 5.0f, lz = pz - 3.0f;
-    float ll = len3(lx, ly, lz);
-    lx = lx / ll; ly = ly / ll; lz = lz / ll;
+    float il = inv_len3(lx, ly, lz);
+    lx = lx * il; ly = ly * il; lz = lz * il;
     float d = dot3(nx, ny, nz, lx, ly, lz);
     return d > 0.05f ? d : 0.05f;
 }
@@ -85,8 +90,8 @@ void fs3d_oracle_raymarch(const uint8_t *grid, uint32_t nx, uint32_t ny, uint32_
             float qx = u * 2.0f - 1.0f;
             float inv_aspect = 1.0f / aspect;
             float qy = (v * 2.0f - 1.0f) * inv_aspect;
-            float ql = len3(qx, qy, 1.0f);
-            float dx = qx / ql, dy = qy / ql, dz = 1.0f / ql;
+            float iq = inv_len3(qx, qy, 1.0f);
+            float dx = qx * iq, dy = qy * iq, dz = 1.0f * iq;
             {
                 float a = cs * dx, b = sn * dz; float rx = a + b;
                 a = cs * dz; b = sn * dx; float rz = a - b;
@@ -103,8 +108,8 @@ void fs3d_oracle_raymarch(const uint8_t *grid, uint32_t nx, uint32_t ny, uint32_
                         float gx = sphere_sdf(cx + s, cy, cz) - sphere_sdf(cx - s, cy, cz);
                         float gy = sphere_sdf(cx, cy + s, cz) - sphere_sdf(cx, cy - s, cz);
                         float gz = sphere_sdf(cx, cy, cz + s) - sphere_sdf(cx, cy, cz - s);
-                        float gl = len3(gx, gy, gz);
-                        gx = gx / gl; gy = gy / gl; gz = gz / gl;
+                        float ig = inv_len3(gx, gy, gz);
+                        gx = gx * ig; gy = gy * ig; gz = gz * ig;
                         r = diffuse_at(cx, cy, cz, gx, gy, gz);
                         depth = t;
                         break;
@@ -202,8 +207,8 @@ void fs3d_oracle_raymarch_pixel(const float pos[3], float aspect, uint32_t W, ui
     float qx = u * 2.0f - 1.0f;
     float inv_aspect = 1.0f / aspect;
     float qy = (v * 2.0f - 1.0f) * inv_aspect;
-    float ql = len3(qx, qy, 1.0f);
-    float dx = qx / ql, dy = qy / ql, dz = 1.0f / ql;
+    float iq = inv_len3(qx, qy, 1.0f);
+    float dx = qx * iq, dy = qy * iq, dz = 1.0f * iq;
     dir_out[0] = dx; dir_out[1] = dy; dir_out[2] = dz;
     *red_out = 0.0f; *iters_out = 64;
     float t = 0.0f;
@@ -215,8 +220,8 @@ void fs3d_oracle_raymarch_pixel(const float pos[3], float aspect, uint32_t W, ui
             float gx = sphere_sdf(cx + s, cy, cz) - sphere_sdf(cx - s, cy, cz);
             float gy = sphere_sdf(cx, cy + s, cz) - sphere_sdf(cx, cy - s, cz);
             float gz = sphere_sdf(cx, cy, cz + s) - sphere_sdf(cx, cy, cz - s);
-            float gl = len3(gx, gy, gz);
-            gx = gx / gl; gy = gy / gl; gz = gz / gl;
+            float ig = inv_len3(gx, gy, gz);
+            gx = gx * ig; gy = gy * ig; gz = gz * ig;
             *red_out = diffuse_at(cx, cy, cz, gx, gy, gz);
             *iters_out = i;
             return;

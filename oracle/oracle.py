@@ -14,7 +14,37 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libfs3d_oracle.so")
 _SOURCES = ["fs3d_oracle.c", "fs3d_sweep.c", "fs3d_raymarch_oracle.c", "Makefile"]
 
+REF_LIB_PATH = os.path.join(HERE, "_ref", "libfs_raymarch_ref.so")
+REFERENCE_ROOT = "/root/reference"
+
 _lib = None
+_ref = None
+
+
+def build_ref(force=False):
+    """Compiles the reference's own shaders/fs_raymarch.frag (with its vendored glm) into oracle/_ref/ — only
+    possible where /root/reference is mounted.  Returns the library path, or None when it cannot be built and no
+    prebuilt copy travelled with the repo."""
+    if os.path.isdir(REFERENCE_ROOT) and (force or not os.path.exists(REF_LIB_PATH)):
+        res = subprocess.run(["make", "-C", HERE, "ref"] + (["-B"] if force else []), capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("building oracle/_ref failed:\n" + res.stdout + res.stderr)
+    return REF_LIB_PATH if os.path.exists(REF_LIB_PATH) else None
+
+
+def ref_frame(pos=(0.0, 0.0, -5.0), aspect=1700.0 / 900.0, width=850, height=450):
+    """Linear RGBA float32 frame (H, W, 4) of the REFERENCE fragment shader itself, or None without oracle/_ref."""
+    global _ref
+    if _ref is None:
+        path = build_ref()
+        if path is None:
+            return None
+        _ref = C.CDLL(path)
+        _ref.fs_raymarch_ref_frame.restype = None
+        _ref.fs_raymarch_ref_frame.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+    out = np.empty((height, width, 4), dtype=np.float32)
+    _ref.fs_raymarch_ref_frame((C.c_float * 3)(*pos), aspect, width, height, out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def build(force=False):

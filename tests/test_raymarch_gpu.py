@@ -120,3 +120,18 @@ def test_one_slab_per_gpu_marches_locally_and_composites(fs3d, oracle):
         w.set_palette(pal)
         cam = dict(pos=(0.3, -0.2, -1.4), yaw_deg=12.0, aspect=16.0 / 9.0, width=160, height=90)
         assert np.array_equal(w.raymarch(mode=fs3d.RM_VOXELS, **cam), oracle.raymarch(g, mode=1, palette=pal, **cam))
+
+
+def test_sdf_mode_equals_the_reference_shader_frames(fs3d):
+    # the CUDA kernel against the output of the reference's own fs_raymarch.frag (compiled with its glm; golden
+    # frames committed under tests/golden/): same hit pixels, same 8-bit colour, pixel for pixel
+    from tests.test_raymarch_oracle import _ref_golden, encode8_linear
+    with fs3d.VoxelWorld(32, 4, 4) as w:
+        for cam, idx, red in _ref_golden():
+            wd, ht = cam["width"], cam["height"]
+            img, depth = w.raymarch(mode=fs3d.RM_SDF_SPHERE, with_depth=True, yaw_deg=0.0, **cam)
+            assert np.array_equal(np.nonzero(np.isfinite(depth).reshape(-1))[0], idx)
+            want = np.zeros(wd * ht, np.uint8)
+            want[idx] = encode8_linear(red)
+            assert np.array_equal(img[..., 0].reshape(-1), want)
+            assert not img[..., 1].any() and not img[..., 2].any() and (img[..., 3] == 255).all()

@@ -84,3 +84,51 @@ def test_voxel_mode_sees_materials(oracle):
     rows_sand = np.nonzero((img[..., 0] > img[..., 2]).any(axis=1))[0]
     rows_stone = np.nonzero(((img[..., 0] > 0) & (np.abs(img[..., 0].astype(int) - img[..., 1].astype(int)) < 3)).any(axis=1))[0]
     assert rows_sand.size and rows_stone.size and rows_sand.min() < rows_stone.max()
+
+
+# ---- pinned against the reference shader ITSELF -------------------------------------------------------------
+# tests/golden/fs_raymarch_ref_frames.npz is the output of /root/reference/shaders/fs_raymarch.frag compiled as C++
+# against the reference's vendored glm (oracle/_ref, tests/golden/make_raymarch_ref_golden.py).
+
+def _ref_golden():
+    z = np.load(os.path.join(GOLDEN, "fs_raymarch_ref_frames.npz"))
+    for k in range(int(z["n"])):
+        c = z[f"cam{k}"]
+        cam = dict(pos=(float(c[0]), float(c[1]), float(c[2])), aspect=float(c[3]), width=int(c[4]), height=int(c[5]))
+        yield cam, z[f"idx{k}"], z[f"red{k}"]
+
+
+def encode8_linear(red):
+    """float32 linear value -> the uint8 both the oracle and the CUDA kernel store (no sRGB)."""
+    r = red.astype(np.float32)
+    return np.where(r >= 1.0, 255, np.floor(r * np.float32(255.0) + np.float32(0.5))).astype(np.uint8)
+
+
+def test_oracle_is_bit_identical_to_the_reference_shader_frames(oracle):
+    for cam, idx, red in _ref_golden():
+        w, h = cam["width"], cam["height"]
+        img, depth = oracle.raymarch(None, mode=0, with_depth=True, **cam)
+        hit = np.isfinite(depth).reshape(-1)
+        assert np.array_equal(np.nonzero(hit)[0], idx), "hit mask differs from fs_raymarch.frag"
+        want = np.zeros(w * h, np.uint8)
+        want[idx] = encode8_linear(red)
+        assert np.array_equal(img[..., 0].reshape(-1), want)
+        assert not img[..., 1].any() and not img[..., 2].any() and (img[..., 3] == 255).all()
+        # the linear float value itself, on a sample of the hit pixels: identical bits
+        for i in idx[:: max(1, idx.size // 400)]:
+            _, r, _ = oracle.raymarch_pixel(int(i % w), int(i // w), pos=cam["pos"], aspect=cam["aspect"], width=w, height=h)
+            assert np.float32(r) == red[np.searchsorted(idx, i)]
+
+
+def test_oracle_matches_live_reference_shader_when_built(oracle):
+    # where /root/reference is mounted (or oracle/_ref travelled with the repo): other cameras, whole frames
+    if oracle.ref_frame(width=8, height=8) is None:
+        pytest.skip("oracle/_ref not available here (needs /root/reference)")
+    rng = np.random.RandomState(5)
+    for _ in range(4):
+        pos = (float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-1.5, 1.5)), float(rng.uniform(-6, -0.7)))
+        cam = dict(pos=pos, aspect=float(rng.uniform(0.8, 2.2)), width=int(rng.randint(40, 300)), height=int(rng.randint(40, 200)))
+        f = oracle.ref_frame(**cam)
+        img, depth = oracle.raymarch(None, mode=0, with_depth=True, **cam)
+        assert np.array_equal(f[..., 0] > 0, np.isfinite(depth))
+        assert np.array_equal(img[..., 0], np.where(f[..., 0] > 0, encode8_linear(f[..., 0]), 0))
