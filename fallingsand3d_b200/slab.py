@@ -121,6 +121,14 @@ class CudaSlabEngine:
     def histogram(self):
         return self.world.histogram()
 
+    def save(self, path):
+        self.world.save(path)
+
+    def load(self, path):
+        """-> (step index, seed) the checkpoint restored."""
+        self.world.load(path)
+        return self.world.step_index, self.world.seed
+
     def reduce_device(self):
         return self.device
 
@@ -206,15 +214,13 @@ class SlabWorld:
 
     def save(self, path):
         """Every rank writes its slab to rank_path(path)."""
-        self.engine.world.save(self.rank_path(path))
+        self.engine.save(self.rank_path(path))
         if self.world_size > 1:
             dist.barrier(group=self.group)
 
     def load(self, path):
         """Every rank restores its slab, step index and seed from rank_path(path); halos are refreshed."""
-        self.engine.world.load(self.rank_path(path))
-        self.step_index = self.engine.world.step_index
-        self.seed = self.engine.world.seed
+        self.step_index, self.seed = self.engine.load(self.rank_path(path))
         if self.world_size > 1:
             self.refresh_halos()
 

@@ -94,6 +94,18 @@ class OracleSlabEngine:
     def histogram(self):
         return self.o.histogram(self.buf[self.cur][1:-1])
 
+    def save(self, path):
+        from fallingsand3d_b200 import checkpoint
+        checkpoint.write(path, self.buf[self.cur][1:-1], nz=self.nz, z_begin=self.zb, step=self.t, seed=self.seed)
+
+    def load(self, path):
+        from fallingsand3d_b200 import checkpoint
+        h, g = checkpoint.read(path)
+        assert (h["nx"], h["ny"], h["nz"], h["z_begin"], h["z_end"]) == (self.nx, self.ny, self.nz, self.zb, self.ze)
+        self.buf[self.cur][1:-1] = g
+        self.t, self.seed = int(h["step"]), int(h["seed"])
+        return self.t, self.seed
+
     def reduce_device(self):
         return torch.device("cpu")
 
