@@ -104,6 +104,25 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """(threads the oracle's OpenMP loops really use, OMP_NUM_THREADS as seen, cpus in the affinity mask)."""
+    from oracle import oracle
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    return oracle.threads(), os.environ.get("OMP_NUM_THREADS"), aff
+
+
+def sample_planes(n, threads, budget_voxels):
+    """z-planes of the CPU sample: about `budget_voxels`, but never fewer than 8 planes per host thread — the oracle's
+    work items are (plane, block-row) pairs and (plane-pair, block-row) pairs, so even the thinnest sample gives every
+    thread thousands of items (round 1 sampled 16 planes for 16-32 threads and parallelised over z only)."""
+    nz = max(budget_voxels // (n * n), 8 * threads, 2)
+    nz = min(n, nz + (nz & 1))
+    return int(nz)
+
+
 def cpu_oracle_rate(nx, ny, nz_sample, steps, seed=1):
     """voxel-updates/s of the CPU oracle on a bounded slab sample of the workload."""
     from oracle import oracle
@@ -116,14 +135,7 @@ def cpu_oracle_rate(nx, ny, nz_sample, steps, seed=1):
     for t in range(1, 1 + steps):
         oracle.step(g, seed, t)
     dt = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
-    omp = os.environ.get("OMP_NUM_THREADS")
-    if omp:
-        cores = min(cores, int(omp))
+    cores = oracle.threads()
     return nx * ny * nz_sample * steps / dt, cores, dt, f"{nx}x{ny}x{nz_sample} slab of the {nx}^3 MIXED_NOISE scene, {steps} steps"
 
 
@@ -141,7 +153,8 @@ def reference_arm(args):
         os.environ.pop("OMP_NUM_THREADS", None)
     from oracle import oracle
     n = args.size
-    nz_sample = max(2, min(n, (1 << 26) // (n * n) or 2))
+    threads, omp_env, affinity = host_threads()
+    nz_sample = sample_planes(n, threads, 1 << 28)      # the same sample the cpu_baseline leg of the GPU arm times
     zlo = n // 2 - nz_sample // 2
     g = oracle.generate(n, n, n, SCENE_MIXED_NOISE, 1, zlo, zlo + nz_sample)
     sample = f"{n}x{n}x{nz_sample} slab (z from {zlo}) of the {n}^3 MIXED_NOISE scene, one oracle step per bench step"
@@ -152,13 +165,7 @@ def reference_arm(args):
     for _ in range(args.steps):
         oracle.step(g, 1, t); t += 1
     dt = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
-    if os.environ.get("OMP_NUM_THREADS"):
-        cores = min(cores, int(os.environ["OMP_NUM_THREADS"]))
+    cores = threads
     value = n * n * nz_sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": args.gpus,
@@ -167,11 +174,151 @@ def reference_arm(args):
         "config": {"workload": f"{n}^3 MIXED_NOISE scene (BASELINE configs[3]); CPU oracle on a bounded sample",
                    "grid": [n, n, n], "sample": sample},
         "cpu_baseline": {"value": value, "unit": "voxel-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "omp_num_threads_env": omp_env, "affinity_cpus": affinity,
                          "note": "the reference has no CPU update to time (SURVEY.md §0); this is the builder-written "
-                                 "CPU oracle of the same schedule, OpenMP over z"},
+                                 "CPU oracle of the same schedule, OpenMP over (plane, block-row) work items"},
         "e2e": {"value": value, "unit": "voxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+class numa_local:
+    """Context manager: binds this thread to the CPUs of the NUMA node GPU `local_rank` hangs off (sysfs
+    local_cpulist of its PCI function) while pinned host memory is allocated and first touched, then restores the
+    affinity mask (so the CPU baseline afterwards still sees every core).  Yields a small report dict."""
+
+    def __init__(self, local_rank):
+        self.local_rank = local_rank
+        self.saved = None
+        self.report = {"bound": False}
+
+    def __enter__(self):
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.local_rank)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            base = os.path.join("/sys/bus/pci/devices", bdf)
+            with open(os.path.join(base, "local_cpulist")) as f:
+                spec = f.read().strip()
+            cpus = set()
+            for part in spec.split(","):
+                if "-" in part:
+                    lo, hi = part.split("-")
+                    cpus.update(range(int(lo), int(hi) + 1))
+                elif part:
+                    cpus.add(int(part))
+            node = None
+            try:
+                with open(os.path.join(base, "numa_node")) as f:
+                    node = int(f.read().strip())
+            except Exception:
+                pass
+            self.saved = os.sched_getaffinity(0)
+            cpus &= self.saved
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                self.report = {"bound": True, "pci": bdf, "numa_node": node, "cpus": len(cpus)}
+        except Exception as e:                     # no sysfs / no permission: allocate wherever the thread runs
+            self.report = {"bound": False, "why": repr(e)[:120]}
+        return self.report
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
+def golden_digest_check(n, total_steps, digest):
+    """Compares the run's digest with the CPU oracle's digest of the same workload at the same step count
+    (tests/golden/bench_digests.json, generated by the oracle on the FULL grid).  Raises on a mismatch."""
+    p = os.path.join(ROOT, "tests", "golden", "bench_digests.json")
+    if not os.path.exists(p):
+        return "no golden file"
+    with open(p) as f:
+        gold = json.load(f)
+    if gold["dims"] != [n, n, n]:
+        return f"no oracle digest for {n}^3 (golden file holds {gold['dims'][0]}^3)"
+    want = gold["digests"].get(str(total_steps))
+    if want is None:
+        return f"no oracle digest for step {total_steps} (have {sorted(int(k) for k in gold['digests'])})"
+    assert int(want, 16) == digest, f"digest after {total_steps} steps {hex(digest)} != CPU oracle's {want}"
+    return f"equals the CPU oracle's digest of the full {n}^3 grid after {total_steps} steps"
+
+
+def big_grid_block(args, world_size, rank, hbm_peak):
+    """BASELINE configs[4]: the 4096^3 RANDOM scene (68.7 G voxels, 2 x 64 GiB) — on ONE 180 GB B200 at N = 1, as z-slabs
+    at N > 1 — so that the driver's records hold T_N at 4096^3 for every N it runs (efficiency = T_1 / (N T_N)), plus
+    one 1920x1080 ray-marched frame.  Same timing rules as the main measurement."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fallingsand3d_b200 as fs3d
+    from fallingsand3d_b200.slab import SlabWorld, slab_bounds
+    n, K = args.big_size, args.big_steps
+    voxels = n * n * n
+    planes = n if world_size == 1 else max(b - a for a, b in slab_bounds(n, world_size))
+    need = 2 * (planes + 2) * n * n + (1 << 30)
+    free, _total = torch.cuda.mem_get_info()
+    ok = torch.tensor([1 if free >= need else 0], device="cuda")
+    if world_size > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        return {"skipped": f"needs {need / 2**30:.0f} GiB per GPU, {free / 2**30:.0f} GiB free"}
+    try:
+        if world_size == 1:
+            w = fs3d.VoxelWorld(n, n, n, seed=1)
+            w.generate(fs3d.SCENE_RANDOM, 1)
+            h0 = w.histogram()
+            w.step(4)
+            w.sync()
+            ms, launches = w.step_timed(K)
+            t0 = time.perf_counter()
+            w.raymarch(width=1920, height=1080, mode=fs3d.RM_VOXELS)
+            frame_ms = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(w.histogram(), h0), "material counts changed: invalid run"
+            digest = w.digest()
+            w.close()
+        else:
+            sw = SlabWorld(n, n, n, seed=1)
+            sw.generate(fs3d.SCENE_RANDOM, 1)
+            h0 = sw.histogram()
+            sw.step(4)
+            sw.sync()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st = sw.engine.stream
+            ev0.record(st)
+            sw.step(K)
+            ev1.record(st)
+            sw.sync()
+            torch.cuda.synchronize()
+            t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            sw.raymarch(width=1920, height=1080, mode=fs3d.RM_VOXELS)        # first frame sets the shared frame up
+            dist.barrier()
+            t0 = time.perf_counter()
+            sw.raymarch(width=1920, height=1080, mode=fs3d.RM_VOXELS)
+            frame_ms = (time.perf_counter() - t0) * 1e3
+            assert np.array_equal(sw.histogram(), h0), "material counts changed: invalid run"
+            digest = sw.digest()
+            launches = (1 if sw.p2p else 3) * ((K + 1) // 2)
+            sw.close()
+    except Exception as e:                                  # the main line must still be printed
+        return {"failed": repr(e)[:200]}
+    achieved = 2.0 * voxels * K / (ms * 1e-3) / 1e9 / world_size
+    return {"grid": [n, n, n], "scene": "RANDOM (25 % sand, 25 % water; BASELINE configs[4], SURVEY.md §8d config 5)",
+            "steps": K, "warmup": 4, "ms_per_step": ms / K, "value": voxels * K / (ms * 1e-3), "unit": "voxel-updates/s",
+            "n_gpus": world_size, "gpu_launches": int(launches), "digest": hex(digest), "digest_step": 4 + K,
+            "roofline_frac_algorithmic": achieved / hbm_peak,
+            "raymarch_1920x1080_ms": frame_ms,
+            "note": "efficiency at N GPUs = (ms_per_step at N = 1) / (N x ms_per_step at N), both from this block; the digest "
+                    "is the same at every N"}
 
 
 def ours(args):
@@ -206,7 +353,7 @@ def ours(args):
         if not args.fused_only:
             w1 = fs3d.VoxelWorld(n, n, n, seed=1, flags=fs3d.FLAG_NO_FUSE)
             w1.generate(SCENE_MIXED_NOISE, 1)
-            w1.step(Wm)
+            w1.step(Wm + (Wm & 1))     # the same (even) warm-up as the fused world: digests are always comparable
             w1.sync()
             ms1, l1 = w1.step_timed(K)
             d1 = w1.digest()
@@ -229,7 +376,7 @@ def ours(args):
         clocks = sampler.stop()
         assert np.array_equal(w.histogram(), h0), "material counts changed: invalid run"
         digest = w.digest()
-        if single is not None and (Wm & 1) == 0:
+        if single is not None:
             assert single["digest"] == hex(digest), "fused and unfused runs disagree"
     else:
         sw = SlabWorld(n, n, n, seed=1)
@@ -241,6 +388,8 @@ def ours(args):
             sampler.wait_ready()
         sw.step(Wm + (Wm & 1))          # same (even) warm-up as at N = 1, so the digest is comparable across N
         sw.sync()
+        if sw.p2p:
+            sw.engine.world.push_wait_stats()       # reset: only the timed region's halo waits are reported
         dist.barrier()
         torch.cuda.synchronize()
         sampler.mark()
@@ -256,6 +405,21 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         clocks = sampler.stop() if rank == 0 else None
+        halo_wait = None
+        if sw.p2p:
+            # what inter-GPU skew cost inside the timed region: time PUSH warps spent blocked on a neighbour's counter
+            ws = torch.tensor(sw.engine.world.push_wait_stats(), device="cuda", dtype=torch.float64)
+            wmax = ws.clone()
+            dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ws, op=dist.ReduceOp.SUM)
+            passes = (K + 1) // 2
+            npairs = (sw.z_end - sw.z_begin) // 2 + 1
+            warps = 148 * 8
+            halo_wait = {"longest_single_wait_ms": float(wmax[1].item()) / 1e6, "blocking_waits_all_ranks": int(ws[2].item()),
+                         "blocked_warp_ms_per_pass_worst_rank": float(wmax[0].item()) / 1e6 / passes,
+                         "lead_in_share_of_iterations": min(1.0, 3.0 * warps / (npairs * (n // 2 + 2))),
+                         "note": "PUSH kernels: warps of a slab's two edge pairs wait (bounded) for the neighbour's previous "
+                                 "pass; lead-in = 3 re-computed iterations per march segment, one segment per resident warp"}
         assert np.array_equal(sw.histogram(), h0), "material counts changed: invalid run"
         digest = sw.digest()
         # kernels per pass per rank: 2 edge launches + 1 interior (NCCL's own kernels not counted); 2 steps per pass
@@ -263,63 +427,73 @@ def ours(args):
 
     value = voxels * K / (ms * 1e-3)
     achieved = 2.0 * voxels * K / (ms * 1e-3) / 1e9 / world_size     # per-GPU algorithmic GB/s
+    total_steps = Wm + (Wm & 1) + K
+    digest_check = golden_digest_check(n, total_steps, digest)
+    p2p = True if world_size == 1 else bool(sw.p2p)
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region (N = 1 path) ----
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    # The call a host-side user makes for a grid that lives in host memory: fs3d_step_host (a rank: fs3d_slab_step_host)
+    # on a pinned buffer.  The product's unit of work is the fused pass, so the headline e2e form is TWO steps per call
+    # (the grid crosses PCIe once in and once out per two steps); the one-step-per-call form is reported beside it.
     e2e = None
     if args.e2e_steps <= 0:
         if world_size == 1:
             w.close()
         else:
             sw.close()
-    elif world_size == 1:
-        # the call a host-side user makes for a grid that lives in host memory: fs3d_step_host, one step
-        # per call, every byte of the grid crosses PCIe in and out inside the timed region
-        host = torch.empty((n, n, n), dtype=torch.uint8, pin_memory=True)
-        hv = host.numpy()
-        w.download(hv)
-        ke = max(1, min(args.e2e_steps, K))
-        w.step_host(hv, hv, 1)                            # warm-up of the copy path
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            w.step_host(hv, hv, 1)                        # returns when the stepped grid is back on the host
-        dt = time.perf_counter() - t0
-        e2e = {"value": voxels * ke / dt, "unit": "voxel-updates/s", "h2d_bytes_per_step": voxels,
-               "d2h_bytes_per_step": voxels, "steps": ke, "ms_per_step": dt * 1e3 / ke,
-               "note": "fs3d_step_host(pinned host grid, 1 step per call): H2D of the whole grid, step kernels and "
-                       "D2H of the result overlap chunk by chunk; wall clock"}
-        # same with two steps per call (the fused pass): half the PCIe bytes per voxel-update
-        if (w.step_index & 1):
-            w.step_host(hv, hv, 1)
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            w.step_host(hv, hv, 2)
-        dt2 = time.perf_counter() - t0
-        e2e["two_steps_per_call"] = {"value": voxels * 2 * ke / dt2, "ms_per_step": dt2 * 1e3 / (2 * ke),
-                                     "h2d_bytes_per_step": voxels // 2, "d2h_bytes_per_step": voxels // 2}
-        del host
-        w.close()
     else:
-        # per rank: upload its slab, step with halo exchange, download its slab
-        zb, ze = sw.z_begin, sw.z_end
-        host = torch.empty((ze - zb, n, n), dtype=torch.uint8, pin_memory=True)
-        hv = host.numpy()
-        hv[...] = sw.download()
         ke = max(1, min(args.e2e_steps, K))
-        sw.step_host(hv, hv, 1)                 # warm-up of the copy path
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            sw.step_host(hv, hv, 1)             # edge planes to the neighbours, then H2D | kernels | D2H chunk by chunk
-        torch.cuda.synchronize()
-        dist.barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = float(dt.item())
-        e2e = {"value": voxels * ke / dt, "unit": "voxel-updates/s", "h2d_bytes_per_step": voxels,
-               "d2h_bytes_per_step": voxels, "steps": ke, "ms_per_step": dt * 1e3 / ke,
-               "note": "per rank: fs3d_slab_step_host on its pinned host slab (edge planes pushed to the neighbours over "
-                       "peer memory, then H2D, step kernels and D2H overlap chunk by chunk); wall clock, max over ranks"}
-        sw.close()
+        with numa_local(local_rank) as numa:         # pinned pages on the GPU's own NUMA node; affinity restored after
+            if world_size == 1:
+                host = torch.empty((n, n, n), dtype=torch.uint8, pin_memory=True)
+                hv = host.numpy()
+                w.download(hv)
+            else:
+                host = torch.empty((sw.z_end - sw.z_begin, n, n), dtype=torch.uint8, pin_memory=True)
+                hv = host.numpy()
+                hv[...] = sw.download()
+        stepper = w if world_size == 1 else sw
+        idx = (lambda: w.step_index) if world_size == 1 else (lambda: sw.step_index)
+
+        def timed(ns):
+            if ns == 2 and (idx() & 1):
+                stepper.step_host(hv, hv, 1)             # a fused pass starts on an even step
+            stepper.step_host(hv, hv, ns)                # warm-up of the copy path
+            if world_size > 1:
+                torch.cuda.synchronize()
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                stepper.step_host(hv, hv, ns)            # returns when the stepped grid is back on the host
+            if world_size > 1:
+                torch.cuda.synchronize()
+                dist.barrier()
+            dt = time.perf_counter() - t0
+            if world_size > 1:
+                tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            return dt
+
+        dt2 = timed(2)
+        dt1 = timed(1)
+        how = ("fs3d_step_host(pinned host grid)" if world_size == 1 else
+               "per rank: fs3d_slab_step_host on its pinned host slab (edge planes pushed to the neighbours over peer "
+               "memory first, one barrier per call)")
+        e2e = {"value": voxels * 2 * ke / dt2, "unit": "voxel-updates/s",
+               "h2d_bytes_per_step": voxels // 2, "d2h_bytes_per_step": voxels // 2,
+               "steps": 2 * ke, "calls": ke, "steps_per_call": 2, "ms_per_step": dt2 * 1e3 / (2 * ke),
+               "bytes_per_call": {"h2d": voxels, "d2h": voxels}, "numa": numa,
+               "note": how + ", two steps (one fused pass) per call: H2D of the whole grid, step kernels and D2H of "
+                       "the result overlap chunk by chunk; wall clock" + (", max over ranks" if world_size > 1 else ""),
+               "one_step_per_call": {"value": voxels * ke / dt1, "ms_per_step": dt1 * 1e3 / ke,
+                                     "h2d_bytes_per_step": voxels, "d2h_bytes_per_step": voxels}}
+        del host
+        stepper.close()
+
+    extra = {}
+    if args.big_steps > 0 and n != args.big_size:
+        extra[f"size_{args.big_size}"] = big_grid_block(args, world_size, rank, hbm_peak)
 
     if rank != 0:
         if world_size > 1:
@@ -330,11 +504,13 @@ def ours(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None
     if world_size == 1 and not args.no_cpu:
-        nz_sample = max(2, min(n, (1 << 28) // (n * n) or 2))     # ~256 Mi voxels per step: 10-30 s in all
+        threads, omp_env, affinity = host_threads()
+        nz_sample = sample_planes(n, threads, 1 << 28)            # >= 256 Mi voxels per step: 10-30 s in all
         rate, cores, dt, sample = cpu_oracle_rate(n, n, nz_sample, args.cpu_steps)
         cpu = {"value": rate, "unit": "voxel-updates/s", "cores": cores, "kind": "port", "sample": sample,
-               "seconds": dt, "note": "builder-written CPU oracle of the same schedule (the reference has no CPU "
-                                      "update, SURVEY.md §0), OpenMP over z"}
+               "seconds": dt, "omp_num_threads_env": omp_env, "affinity_cpus": affinity,
+               "note": "builder-written CPU oracle of the same schedule (the reference has no CPU update, SURVEY.md §0), "
+                       "OpenMP over (plane, block-row) work items"}
 
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -348,10 +524,12 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"{n}^3 MIXED_NOISE scene (BASELINE configs[3]: 2048^3 mixed sand/water/stone), "
                                f"generated on device, skipping off",
-                   "grid": [n, n, n], "parallelism": (f"z-slabs x{world_size}, halo pushed over NVLink peer memory inside the step kernel"
-                                   if world_size > 1 else "single GPU"),
+                   "grid": [n, n, n],
+                   "parallelism": ("single GPU" if world_size == 1 else
+                                   f"z-slabs x{world_size}, halo pushed over NVLink peer memory inside the step kernel" if p2p else
+                                   f"z-slabs x{world_size}, halo planes exchanged with NCCL send/recv on a side stream"),
                    "l2": "inputs larger than L2 (grid %.1f GiB per buffer vs 126 MB L2); no flush" % (voxels / 2**30),
-                   "digest": hex(digest)},
+                   "digest": hex(digest), "digest_step": total_steps, "digest_check": digest_check},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -361,6 +539,8 @@ def ours(args):
                              "voxel TWO steps while moving ~2 B per voxel, so frac can exceed 1: the real DRAM bytes "
                              "are `traffic`; `single_step` is the unfused kernel the 2 B/update roofline describes"},
         "single_step": single,
+        "halo_wait": halo_wait if world_size > 1 else None,
+        "extra": extra,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
@@ -381,6 +561,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused-only", action="store_true", help="skip the unfused single-step measurement")
+    ap.add_argument("--big-size", type=int, default=4096, help="grid edge of the extra large-grid block (BASELINE configs[4])")
+    ap.add_argument("--big-steps", type=int, default=20, help="timed steps of the extra large-grid block; 0 = skip it")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -57,7 +57,7 @@ struct Slab {
     int num_sms = 0;
     int blocks_per_sm[2][2][2][2][2] = {};   // [PUSH][NS-1][SKIP][OX][TODD] for this world's J
     // fused halo push (one process per GPU, CUDA IPC): my arrival counters and the neighbours' memory
-    unsigned long long *d_flags = nullptr;     // [0] iterations delivered from below, [1] from above
+    unsigned long long *d_flags = nullptr;     // [0] iterations delivered from below, [1] from above, [2] watchdog error word, [3..5] wait statistics
     struct Peer {
         uint8_t *buf[2] = {nullptr, nullptr};  // neighbour's two slab buffers (IPC-mapped)
         unsigned long long *flags = nullptr;   // neighbour's d_flags
@@ -69,14 +69,15 @@ struct Slab {
     struct Frame {
         unsigned long long *base = nullptr;   // slot 0; mine if `owner`, else the compositor's memory mapped through CUDA IPC
         bool owner = false;
+        bool ipc = false;                     // mapped through CUDA IPC (closed on destroy); neither: borrowed from a world of this process
         uint32_t width = 0, height = 0, nslots = 0, slot = 0;
         uint32_t *d_rgba = nullptr;           // compositor only: resolved image
     } frame;
     // settled-tile skipping
-    uint8_t *d_skip = nullptr;
-    uint32_t *d_last_active = nullptr;
-    unsigned long long *d_tiles_run = nullptr;
-    uint32_t *d_runs = nullptr, *d_nruns = nullptr;   // live march segments of the launch in flight
+    uint32_t *d_last_active = nullptr;         // non-null <=> FS3D_FLAG_SKIP_SETTLED
+    unsigned long long *d_stats = nullptr;     // [3][2] (tiles live, tiles total), rotating per pass (skip_plan_kernel)
+    uint32_t *d_runs = nullptr, *d_nruns = nullptr;   // live march segments of the launch in flight; nruns[2] rotates per launch
+    uint64_t plan_pass = 0, plan_launch = 0;   // passes / SKIP launches planned so far (indices of the rotating counters)
     uint32_t nztiles = 0, nytiles = 0;
 };
 
@@ -99,6 +100,9 @@ struct fs3d_world {
     bool p2p = false;            // slab world with IPC-attached neighbours: fused halo push, fs3d_step allowed
     unsigned long long wait_target = 0;   // iterations each neighbour has delivered before the next pass
     bool ghosts_stale = false;   // slab world after fs3d_slab_step_host: fs3d_slab_push_halos must run before fs3d_step
+    unsigned long long push_timeout_ns = 20000ull * 1000000ull;   // watchdog of the fused halo push (FS3D_PUSH_TIMEOUT_MS)
+    bool force_live = false;     // fs3d_step_host in flight: settled-tile plans treat every tile as live
+    bool failed = false;         // the watchdog fired: cells are undefined, stepping is refused
 };
 
 namespace fs3d {
@@ -173,21 +177,20 @@ static int init_slab(fs3d_world *w, Slab &s) {
                         FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), step_threads(w->jidx), smem));
                         s.blocks_per_sm[pu][ns - 1][sk][ox][td] = std::max(nb, 1);
                     }
-    FS3D_CUDA(cudaMalloc(&s.d_flags, 2 * sizeof(unsigned long long)));
-    FS3D_CUDA(cudaMemsetAsync(s.d_flags, 0, 2 * sizeof(unsigned long long), s.s_main));
+    FS3D_CUDA(cudaMalloc(&s.d_flags, 8 * sizeof(unsigned long long)));
+    FS3D_CUDA(cudaMemsetAsync(s.d_flags, 0, 8 * sizeof(unsigned long long), s.s_main));
     if (w->desc.flags & FS3D_FLAG_SKIP_SETTLED) {
         s.nztiles = (s.nzl + (1u << ZTILE_LOG2) - 1) >> ZTILE_LOG2;
         s.nytiles = (w->desc.ny + (1u << YTILE_LOG2) - 1) >> YTILE_LOG2;
         const size_t nt = (size_t)s.nztiles * s.nytiles;
-        FS3D_CUDA(cudaMalloc(&s.d_skip, nt));
         FS3D_CUDA(cudaMalloc(&s.d_last_active, nt * sizeof(uint32_t)));
-        FS3D_CUDA(cudaMalloc(&s.d_tiles_run, 2 * sizeof(unsigned long long)));
+        FS3D_CUDA(cudaMalloc(&s.d_stats, 6 * sizeof(unsigned long long)));
         const size_t max_runs = ((size_t)s.nzl / 2 + 2) * (((size_t)w->desc.ny / 2 + 2) / (1u << (YTILE_LOG2 - 1)) + 2);
         FS3D_CUDA(cudaMalloc(&s.d_runs, max_runs * 3 * sizeof(uint32_t)));
-        FS3D_CUDA(cudaMalloc(&s.d_nruns, sizeof(uint32_t)));
-        FS3D_CUDA(cudaMemsetAsync(s.d_skip, 0, nt, s.s_main));
+        FS3D_CUDA(cudaMalloc(&s.d_nruns, 2 * sizeof(uint32_t)));
         FS3D_CUDA(cudaMemsetAsync(s.d_last_active, 0, nt * sizeof(uint32_t), s.s_main));
-        FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, 2 * sizeof(unsigned long long), s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_stats, 0, 6 * sizeof(unsigned long long), s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_nruns, 0, 2 * sizeof(uint32_t), s.s_main));
     }
     // both buffers start as EMPTY with STONE ghost planes (closed box / not-yet-exchanged halo)
     for (int b = 0; b < 2; ++b) {
@@ -209,16 +212,15 @@ static void free_slab(Slab &s) {
         for (int b = 0; b < 2; ++b) if (pr->buf[b]) cudaIpcCloseMemHandle(pr->buf[b]);
         if (pr->flags) cudaIpcCloseMemHandle(pr->flags);
     }
-    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else cudaIpcCloseMemHandle(s.frame.base); }
+    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else if (s.frame.ipc) cudaIpcCloseMemHandle(s.frame.base); }
     if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
     if (s.d_flags) cudaFree(s.d_flags);
     if (s.d_scratch) cudaFree(s.d_scratch);
     if (s.d_img) cudaFree(s.d_img);
     if (s.d_palette) cudaFree(s.d_palette);
     if (s.d_thr) cudaFree(s.d_thr);
-    if (s.d_skip) cudaFree(s.d_skip);
     if (s.d_last_active) cudaFree(s.d_last_active);
-    if (s.d_tiles_run) cudaFree(s.d_tiles_run);
+    if (s.d_stats) cudaFree(s.d_stats);
     if (s.d_runs) cudaFree(s.d_runs);
     if (s.d_nruns) cudaFree(s.d_nruns);
     cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_out_lo, s.ev_out_hi, s.ev_t0, s.ev_t1};
@@ -240,6 +242,10 @@ static void default_palette(float *p) {
 }
 
 static int finish_create(fs3d_world *w) {
+    if (const char *ms = std::getenv("FS3D_PUSH_TIMEOUT_MS")) {
+        const long long v = std::atoll(ms);
+        if (v > 0) w->push_timeout_ns = (unsigned long long)v * 1000000ull;
+    }
     const uint32_t wpr = w->desc.nx / 32;
     w->jidx = wpr <= 32 ? 0 : (wpr <= 64 ? 1 : 2);
     w->lpr = wpr < 32 ? wpr : 32;
@@ -279,8 +285,8 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     p.key_zy = step_key(w->desc.seed, t, 1);
     p.key_xy2 = step_key(w->desc.seed, t + 1, 0);
     p.key_zy2 = step_key(w->desc.seed, t + 1, 1);
-    const int sk = s.d_skip ? 1 : 0;
-    p.skip = s.d_skip; p.last_active = s.d_last_active;
+    const int sk = s.d_last_active ? 1 : 0;
+    p.last_active = s.d_last_active;
     p.ytile_log2 = YTILE_LOG2; p.ztile_log2 = ZTILE_LOG2; p.nytiles = s.nytiles;
     p.step_plus1 = (uint32_t)(t + (uint64_t)ns);
     if (push) {
@@ -296,6 +302,8 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
         }
         p.my_flags = s.d_flags;
         p.wait_target = w->wait_target;
+        p.push_err = s.d_flags + 2;
+        p.push_timeout_ns = w->push_timeout_ns;
     }
 
     const uint64_t npg = ((uint64_t)(pe - pb) + w->groups - 1) / w->groups;
@@ -309,15 +317,24 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     uint64_t blocks = std::min<uint64_t>(max_blocks, (want_warps + warps_per_block - 1) / warps_per_block);
     blocks = std::max<uint64_t>(blocks, 1);
     if (sk) {
-        // compact the live (pair group, y-block) segments of this launch into the run list the warps share out
-        const uint32_t units = (uint32_t)(blocks * warps_per_block / warps_per_pair(w->jidx));
-        FS3D_CUDA(cudaMemsetAsync(s.d_nruns, 0, sizeof(uint32_t), s.s_main));
-        skip_runs_kernel<<<(unsigned)((npg + 3) / 4), 128, 0, s.s_main>>>(
-            s.d_skip, s.nytiles, ZTILE_LOG2, YTILE_LOG2 - 1, s.nzl, L.lz_first, pb, pe, w->groups, p.nit, (uint32_t)ns, units,
-            s.d_tiles_run, s.d_runs, s.d_nruns);
+        // plan: compact the live (pair group, y-block) segments of this launch into the run list the warps share out
+        PlanParams q{};
+        q.last_active = s.d_last_active;
+        q.nztiles = s.nztiles; q.nytiles = s.nytiles; q.ztile_log2 = ZTILE_LOG2; q.blk_log2 = YTILE_LOG2 - 1;
+        q.nzl = s.nzl; q.lz_first = L.lz_first; q.pair_begin = pb; q.pair_end = pe; q.groups = w->groups;
+        q.nit = p.nit; q.ns = (uint32_t)ns;
+        q.nw = (uint32_t)(blocks * warps_per_block / warps_per_pair(w->jidx));
+        q.t_now = (uint32_t)t;
+        q.has_lo_neighbour = s.z0 > 0; q.has_hi_neighbour = s.z0 + s.nzl < w->desc.nz;
+        q.force_live = w->force_live ? 1 : 0;
+        const uint64_t k = s.plan_pass;           // begin_skip_pass advanced it for this pass
+        q.stats_prev = s.d_stats + 2 * ((k + 2) % 3); q.stats_cur = s.d_stats + 2 * (k % 3); q.stats_next = s.d_stats + 2 * ((k + 1) % 3);
+        q.runs = s.d_runs; q.nruns = s.d_nruns + (s.plan_launch & 1); q.nruns_next = s.d_nruns + ((s.plan_launch + 1) & 1);
+        s.plan_launch++;
+        skip_plan_kernel<<<(unsigned)((npg + 3) / 4), 128, 0, s.s_main>>>(q);
         FS3D_CUDA(cudaGetLastError());
         w->launches++;
-        p.runs = s.d_runs; p.nruns = s.d_nruns;
+        p.runs = q.runs; p.nruns = q.nruns;
     }
     step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, step_smem(w->jidx, push), s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
@@ -325,16 +342,10 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
     return FS3D_OK;
 }
 
-// settled-tile skipping: recompute the skip map of one slab for the step about to run
-static int launch_skip_map(fs3d_world *w, Slab &s) {
-    if (!s.d_skip) return FS3D_OK;
-    const uint32_t nt = s.nztiles * s.nytiles;
-    FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, sizeof(unsigned long long), s.s_main));
-    const int has_lo = s.z0 > 0, has_hi = s.z0 + s.nzl < w->desc.nz;
-    skip_map_kernel<<<std::max(1u, std::min((nt + 255u) / 256u, 1024u)), 256, 0, s.s_main>>>(
-        s.d_last_active, s.d_skip, s.nztiles, s.nytiles, (uint32_t)w->step, has_lo, has_hi, s.d_tiles_run);
-    FS3D_CUDA(cudaGetLastError());
-    w->launches++;
+// settled-tile skipping: a new pass begins on this slab (the statistics counters rotate; the plan itself is made by
+// skip_plan_kernel in front of every SKIP launch, straight from the tiles' last_active stamps)
+static int launch_skip_map(fs3d_world *, Slab &s) {
+    if (s.d_last_active) s.plan_pass++;
     return FS3D_OK;
 }
 
@@ -342,7 +353,7 @@ static int launch_skip_map(fs3d_world *w, Slab &s) {
 // every tile counts as active "just now", so the next four steps run everywhere
 static int touch_all_tiles(fs3d_world *w) {
     for (auto &s : w->slabs) {
-        if (!s.d_skip) continue;
+        if (!s.d_last_active) continue;
         FS3D_CUDA(cudaSetDevice(s.device));
         const uint64_t nt = (uint64_t)s.nztiles * s.nytiles;
         // last_active holds (step + 1); "active at step - 1" = step; a fresh world (step 0) holds 0
@@ -461,13 +472,34 @@ static int refresh_ghosts(fs3d_world *w) {
     return FS3D_OK;
 }
 
+// fused halo push: did a kernel give up waiting for a neighbour (step_kernel.cuh, wait_arrival)?
+static int check_push_watchdog(fs3d_world *w) {
+    if (!w->p2p || w->failed) return FS3D_OK;      // reported once; afterwards only stepping is refused
+    for (auto &s : w->slabs) {
+        unsigned long long e = 0;
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaMemcpy(&e, s.d_flags + 2, sizeof(e), cudaMemcpyDeviceToHost));
+        if (e == 0) continue;
+        w->failed = true;
+        char msg[400];
+        std::snprintf(msg, sizeof(msg),
+                      "fused halo push: slab z [%u, %u) waited more than %llu ms for its %s%s%s neighbour to deliver (arrival "
+                      "target %llu): the neighbour rank died or the ranks issued different fs3d_step sequences; this world's "
+                      "cells are undefined and it will not step again (destroy and re-create the slab worlds)",
+                      s.z0, s.z0 + s.nzl, w->push_timeout_ns / 1000000ull, (e & 1) ? "lower" : "", (e & 3) == 3 ? " and " : "",
+                      (e & 2) ? "upper" : "", e >> 8);
+        return fail(FS3D_ERR_CUDA, msg);
+    }
+    return FS3D_OK;
+}
+
 static int sync_all(fs3d_world *w) {
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
         FS3D_CUDA(cudaStreamSynchronize(s.s_main));
         FS3D_CUDA(cudaStreamSynchronize(s.s_comm));
     }
-    return FS3D_OK;
+    return check_push_watchdog(w);
 }
 
 static Slab *slab_of_z(fs3d_world *w, uint32_t z) {
@@ -499,7 +531,7 @@ static void rm_camera(const fs3d_world *w, const fs3d_camera *cam, uint32_t widt
 static int ensure_frame(Slab &s, uint32_t width, uint32_t height, uint32_t n_slots) {
     if (s.frame.base && s.frame.owner && s.frame.width == width && s.frame.height == height && s.frame.nslots == n_slots)
         return FS3D_OK;
-    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else cudaIpcCloseMemHandle(s.frame.base); }
+    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else if (s.frame.ipc) cudaIpcCloseMemHandle(s.frame.base); }
     if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
     s.frame = Slab::Frame();
     const size_t npix = (size_t)width * height;
@@ -702,7 +734,13 @@ int fs3d_create(const fs3d_desc *desc, fs3d_world **out) {
     for (int i = 0; i < n && push_ok; ++i)
         for (int j = 0; j < n && push_ok; ++j) {
             if (i == j) continue;
-            if (w->devices[i] == w->devices[j]) push_ok = false;
+            if (w->devices[i] == w->devices[j]) {
+                // FS3D_FLAG_PEER_PUSH_SHARED_DEVICE: run the PUSH kernels even so (what a one-GPU box needs to test them).
+                // It cannot deadlock: only the warps of a slab's two edge pairs ever wait, every other CTA of a kernel
+                // retires, so the neighbour's previous pass always finds SMs.
+                if (!(desc->flags & FS3D_FLAG_PEER_PUSH_SHARED_DEVICE)) push_ok = false;
+                continue;
+            }
             if (std::abs(i - j) == 1) {
                 int can = 0;
                 cudaDeviceCanAccessPeer(&can, w->devices[i], w->devices[j]);
@@ -777,6 +815,8 @@ int fs3d_step(fs3d_world *w, uint32_t n_steps) {
                                           "or through fs3d_step after fs3d_slab_ipc_attach");
     if (w->ghosts_stale)
         return fail(FS3D_ERR_UNSUPPORTED, "after fs3d_slab_step_host call fs3d_slab_push_halos on every rank (and barrier) before fs3d_step");
+    if (w->failed)
+        return fail(FS3D_ERR_CUDA, "the halo-push watchdog fired earlier: cells are undefined; destroy and re-create the slab worlds");
     uint32_t left = n_steps;
     while (left > 0) {
         // steps 2k and 2k + 1 share the z-pairing and x-offset, so they fuse into one pass
@@ -997,10 +1037,10 @@ int fs3d_activity(fs3d_world *w, uint64_t *tiles_run, uint64_t *tiles_total) {
     int rc = sync_all(w);
     if (rc) return rc;
     for (auto &s : w->slabs) {
-        if (!s.d_skip) { *tiles_run += 1; *tiles_total += 1; continue; }   // skipping off: everything runs
+        if (!s.d_last_active) { *tiles_run += 1; *tiles_total += 1; continue; }   // skipping off: everything runs
         FS3D_CUDA(cudaSetDevice(s.device));
         unsigned long long st[2] = {0, 0};
-        FS3D_CUDA(cudaMemcpy(st, s.d_tiles_run, sizeof(st), cudaMemcpyDeviceToHost));
+        FS3D_CUDA(cudaMemcpy(st, s.d_stats + 2 * (s.plan_pass % 3), sizeof(st), cudaMemcpyDeviceToHost));
         *tiles_run += st[0];
         *tiles_total += st[1] ? st[1] : (unsigned long long)s.nztiles * s.nytiles;
     }
@@ -1142,10 +1182,8 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
     }
     uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
     FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
-    if (s.d_skip) {   // the grid comes from the host: nothing is known to be static
-        FS3D_CUDA(cudaMemsetAsync(s.d_skip, 0, (size_t)s.nztiles * s.nytiles, s.s_main));
-        FS3D_CUDA(cudaMemsetAsync(s.d_tiles_run, 0, 2 * sizeof(unsigned long long), s.s_main));
-    }
+    launch_skip_map(w, s);
+    w->force_live = true;            // the grid comes from the host: nothing is known to be static
     FS3D_CUDA(cudaEventRecord(s.ev_t0, s.s_main));
     FS3D_CUDA(cudaStreamWaitEvent(s.s_h2d, s.ev_t0, 0));
     uint8_t *src = s.buf[w->cur], *dst = s.buf[w->cur ^ 1];
@@ -1161,12 +1199,13 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
         validate_kernel<<<grid_for(bytes / 16, s), 256, 0, s.s_main>>>(src + off, bytes / 16, flag);
         FS3D_CUDA(cudaGetLastError());
         rc = launch_pairs(w, s, p0, p1, ns);
-        if (rc) return rc;
+        if (rc) { w->force_live = false; return rc; }
         FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c + 1], s.s_main));
         FS3D_CUDA(cudaStreamWaitEvent(s.s_d2h, s.ev_chunk[2 * c + 1], 0));
         FS3D_CUDA(cudaMemcpyAsync(host_out + pb * (size_t)(lo - 1), dst + off, bytes, cudaMemcpyDeviceToHost, s.s_d2h));
         w->launches++;   // validate_kernel
     }
+    w->force_live = false;
     uint32_t bad = 0;
     FS3D_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, s.s_main));
     FS3D_CUDA(cudaStreamSynchronize(s.s_main));
@@ -1275,6 +1314,60 @@ int fs3d_slab_ipc_attach(fs3d_world *w, const void *lower_blob, const void *uppe
     return FS3D_OK;
 }
 
+// The same wiring for slab worlds that live in ONE process (one host thread per GPU, or several slabs on one GPU in
+// the tests): plain pointers instead of CUDA IPC handles.
+static int attach_local_peer(Slab &s, Slab::Peer &pr, fs3d_world *nb, uint32_t expect_z, bool expect_end, int my_cur) {
+    if (!nb->external || nb->slabs.size() != 1) return fail(FS3D_ERR_UNSUPPORTED, "neighbour must be a world made by fs3d_create_slab");
+    Slab &d = nb->slabs[0];
+    if ((expect_end ? d.z0 + d.nzl : d.z0) != expect_z) return fail(FS3D_ERR_INVALID_ARG, "neighbour world is not the adjacent slab");
+    if (nb->cur != my_cur) return fail(FS3D_ERR_INVALID_ARG, "neighbour's buffer parity differs (edit worlds collectively)");
+    if (d.device != s.device) {
+        int can = 0;
+        FS3D_CUDA(cudaDeviceCanAccessPeer(&can, s.device, d.device));
+        if (!can) return fail(FS3D_ERR_UNSUPPORTED, "no peer access to the neighbour's device");
+        cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FS3D_CUDA(e);
+        cudaGetLastError();
+    }
+    pr.buf[0] = d.buf[0]; pr.buf[1] = d.buf[1]; pr.flags = d.d_flags; pr.nzl = d.nzl;
+    pr.valid = true; pr.ipc = false;
+    return FS3D_OK;
+}
+
+int fs3d_slab_attach_local(fs3d_world *w, fs3d_world *lower, fs3d_world *upper) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (w->slabs.size() != 1 || !w->external) return fail(FS3D_ERR_UNSUPPORTED, "needs a world made by fs3d_create_slab");
+    if (w->p2p) return fail(FS3D_ERR_INVALID_ARG, "neighbours already attached");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if ((lower != nullptr) != (s.z0 > 0)) return fail(FS3D_ERR_INVALID_ARG, "lower neighbour must be given iff z_begin > 0");
+    if ((upper != nullptr) != (s.z0 + s.nzl < w->desc.nz)) return fail(FS3D_ERR_INVALID_ARG, "upper neighbour must be given iff z_end < nz");
+    if (lower) { int rc = attach_local_peer(s, s.peer_lo, lower, s.z0, true, w->cur); if (rc) return rc; }
+    if (upper) { int rc = attach_local_peer(s, s.peer_hi, upper, s.z0 + s.nzl, false, w->cur); if (rc) { s.peer_lo = Slab::Peer(); return rc; } }
+    FS3D_CUDA(cudaMemset(s.d_flags, 0, 8 * sizeof(unsigned long long)));
+    w->wait_target = 0;
+    w->p2p = true;
+    return FS3D_OK;
+}
+
+/* What the halo waits cost so far (and resets the counters): out[0] = ns spent waiting for a neighbour's arrival counter,
+ * summed over the warps that really blocked; out[1] = the longest single wait; out[2] = number of blocking waits. */
+int fs3d_push_wait_stats(fs3d_world *w, uint64_t out[3]) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    out[0] = out[1] = out[2] = 0;
+    if (!w->p2p) return FS3D_OK;
+    int rc = sync_all(w);
+    if (rc) return rc;
+    for (auto &s : w->slabs) {
+        unsigned long long v[3] = {0, 0, 0};
+        FS3D_CUDA(cudaSetDevice(s.device));
+        FS3D_CUDA(cudaMemcpy(v, s.d_flags + 3, sizeof(v), cudaMemcpyDeviceToHost));
+        FS3D_CUDA(cudaMemset(s.d_flags + 3, 0, sizeof(v)));
+        out[0] += v[0]; out[1] = std::max<uint64_t>(out[1], v[1]); out[2] += v[2];
+    }
+    return FS3D_OK;
+}
+
 /* Copies this slab's two edge planes of the FRONT buffer into the neighbours' ghost planes (after
  * generate / upload / edits).  Every rank calls it, then all ranks barrier before the next step. */
 int fs3d_slab_push_halos(fs3d_world *w) {
@@ -1333,9 +1426,34 @@ int fs3d_frame_attach(fs3d_world *w, const void *blob, uint32_t slot) {
         s.frame.slot = slot;
         return FS3D_OK;
     }
-    if (s.frame.base) { cudaIpcCloseMemHandle(s.frame.base); s.frame = Slab::Frame(); }
+    if (s.frame.base) { if (s.frame.ipc) cudaIpcCloseMemHandle(s.frame.base); s.frame = Slab::Frame(); }
     FS3D_CUDA(cudaIpcOpenMemHandle((void **)&s.frame.base, b.mem, cudaIpcMemLazyEnablePeerAccess));
+    s.frame.ipc = true;
     s.frame.width = b.width; s.frame.height = b.height; s.frame.nslots = b.nslots; s.frame.slot = slot;
+    return FS3D_OK;
+}
+
+int fs3d_frame_attach_local(fs3d_world *w, fs3d_world *owner, uint32_t slot) {
+    if (!w || !owner) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    Slab &o = owner->slabs[0];
+    if (!o.frame.base || !o.frame.owner) return fail(FS3D_ERR_UNSUPPORTED, "owner has no frame (call fs3d_frame_export on it first)");
+    if (slot >= o.frame.nslots) return fail(FS3D_ERR_OUT_OF_RANGE, "slot outside the frame");
+    Slab &s = w->slabs[0];
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if (w == owner) { s.frame.slot = slot; return FS3D_OK; }
+    if (s.device != o.device) {
+        int can = 0;
+        FS3D_CUDA(cudaDeviceCanAccessPeer(&can, s.device, o.device));
+        if (!can) return fail(FS3D_ERR_UNSUPPORTED, "no peer access to the frame owner's device");
+        cudaError_t e = cudaDeviceEnablePeerAccess(o.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) FS3D_CUDA(e);
+        cudaGetLastError();
+    }
+    if (s.frame.base) { if (s.frame.owner) cudaFree(s.frame.base); else if (s.frame.ipc) cudaIpcCloseMemHandle(s.frame.base); }
+    if (s.frame.d_rgba) cudaFree(s.frame.d_rgba);
+    s.frame = Slab::Frame();
+    s.frame.base = o.frame.base;            // borrowed: the owner frees it
+    s.frame.width = o.frame.width; s.frame.height = o.frame.height; s.frame.nslots = o.frame.nslots; s.frame.slot = slot;
     return FS3D_OK;
 }
 

@@ -43,13 +43,12 @@ struct StepParams {
     uint32_t key_xy, key_zy; // SCHEDULE.md §3 key(seed, t, axis)
     uint32_t key_xy2, key_zy2; // keys of step t + 1 (NS = 2 only)
     // settled-tile skipping (SKIP = 1 instantiations only)
-    const uint8_t *skip;     // [ztiles][ytiles] 1 = tile provably static this step
     uint32_t *last_active;   // [ztiles][ytiles] (step + 1) of the last enabled block seen in the tile
     uint32_t ytile_log2;     // y-tile height = 1 << ytile_log2 planes (>= 2)
     uint32_t ztile_log2;     // z-tile depth = 1 << ztile_log2 owned planes
     uint32_t nytiles;
     uint32_t step_plus1;     // (uint32)(t + NS)
-    const uint32_t *runs;    // [n][3] = (pair group, it_a, it_b): the live march segments of this launch, built by skip_runs_kernel
+    const uint32_t *runs;    // [n][3] = (pair group, it_a, it_b): the live march segments of this launch, built by skip_plan_kernel
     const uint32_t *nruns;
     // fused halo push over peer memory (PUSH = 1 instantiations only): the warps that compute this
     // slab's first / last owned plane also store it into the z-neighbour's ghost plane (its dst
@@ -62,6 +61,12 @@ struct StepParams {
     unsigned long long *peer_hi_flag;     // neighbour above: its arrive[0]
     const unsigned long long *my_flags;   // arrive[0] (from below), arrive[1] (from above)
     unsigned long long wait_target;       // cumulative iterations the neighbours must have delivered
+    // watchdog of that wait: a neighbour that died, missed a pass or was stepped a different number of times would
+    // otherwise hang this kernel (and every later fs3d_sync / fs3d_destroy) forever.  A warp that has waited
+    // push_timeout_ns sets push_err (bit 0: the neighbour below, bit 1: above; bits 8..: the pass it waited for) and
+    // goes on; every later wait of this world falls through at once, and the host turns the word into FS3D_ERR_CUDA.
+    unsigned long long *push_err;
+    unsigned long long push_timeout_ns;
 };
 
 // cache-policy qualifiers of the streaming accesses (tuning hooks; defaults measured best)
@@ -87,6 +92,43 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait for a z-neighbour's arrival counter (PUSH kernels).  side: 0 = the neighbour below, 1 = above.
+// err[0] = watchdog word; err[1..3] = statistics of the waits that really blocked (ns summed over warps, longest
+// single wait, number of waits) — what inter-GPU skew costs, read back through fs3d_push_wait_stats.
+__device__ __forceinline__ void wait_arrival(const unsigned long long *flag, unsigned long long target,
+                                             unsigned long long *err, unsigned long long timeout_ns, unsigned side) {
+    if (ld_acquire_sys(flag) >= target) return;
+    const unsigned long long t0 = global_ns();
+    unsigned spins = 0;
+    bool gave_up = false;
+    while (ld_acquire_sys(flag) < target) {
+        __nanosleep(64);
+        if ((++spins & 63u) == 0u) {
+            if (ld_relaxed_u64(err) != 0ull) { gave_up = true; break; }   // this world already failed: do not wait again
+            if (global_ns() - t0 > timeout_ns) {
+                atomicOr(err, (1ull << side) | (target << 8));
+                gave_up = true;
+                break;
+            }
+        }
+    }
+    if ((threadIdx.x & 31u) == 0u && !gave_up) {
+        const unsigned long long dt = global_ns() - t0;
+        atomicAdd(err + 1, dt);
+        atomicMax(err + 2, dt);
+        atomicAdd(err + 3, 1ull);
+    }
 }
 __device__ __forceinline__ void st256(uint8_t *p, const uint32_t (&r)[8]) {
     asm volatile("st.global" FS3D_ST_POLICY ".v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -198,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     const uint64_t total = (uint64_t)npg * p.nit;
     // Work split.  Without skipping every iteration costs the same, so the (pair-group x iteration)
     // space is cut into equal contiguous ranges, one per resident warp (no tail, one lead-in each).
-    // With skipping only the live segments exist as work: skip_runs_kernel compacts them into a list of
+    // With skipping only the live segments exist as work: skip_plan_kernel compacts them into a list of
     // runs (a few y-blocks of one pair group each) that is dealt round-robin to the warps.
     const uint32_t nruns = SKIP ? *p.nruns : 0xFFFFFFFFu;
     uint32_t run = gw;
@@ -272,8 +314,8 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
             // pairs that read a ghost plane, or write a neighbour's, wait for that neighbour's previous pass
             const bool near_lo = pair_ok && lzl <= 1u && p.peer_lo_flag != nullptr;
             const bool near_hi = pair_ok && lzl + 1u >= p.nzl && p.peer_hi_flag != nullptr;
-            if (__any_sync(ONES, near_lo)) while (ld_acquire_sys(p.my_flags + 0) < p.wait_target) __nanosleep(64);
-            if (__any_sync(ONES, near_hi)) while (ld_acquire_sys(p.my_flags + 1) < p.wait_target) __nanosleep(64);
+            if (__any_sync(ONES, near_lo)) wait_arrival(p.my_flags + 0, p.wait_target, p.push_err, p.push_timeout_ns, 0u);
+            if (__any_sync(ONES, near_hi)) wait_arrival(p.my_flags + 1, p.wait_target, p.push_err, p.push_timeout_ns, 1u);
             __syncwarp();
         }
 
@@ -580,81 +622,93 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     }
 }
 
-// skip[t] = 1 iff tile t and its 8 neighbours in (z-tile, y-tile) space saw no enabled block during the
-// last four steps (all four offset phases), so nothing in or around it can change at step `t_now`.
-// Edge z-tiles next to another slab are never skipped (the neighbour's activity is not visible here).
-__global__ void skip_map_kernel(const uint32_t *last_active, uint8_t *skip, uint32_t nztiles, uint32_t nytiles,
-                                uint32_t t_now, int has_lo_neighbour, int has_hi_neighbour,
-                                unsigned long long *stats /* [0] tiles run, [1] tiles total (overwritten) */) {
-    const uint32_t n = nztiles * nytiles;
-    uint32_t run = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int zt = (int)(i / nytiles), yt = (int)(i % nytiles);
-        uint32_t newest = 0;   // largest (last active step + 1) in the 3x3 neighbourhood, relative age below
-        bool quiet = true;
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy) {
-                int z = zt + dz, y = yt + dy;
-                if (z < 0 || z >= (int)nztiles || y < 0 || y >= (int)nytiles) continue;
-                uint32_t la = last_active[(size_t)z * nytiles + y];
-                // quiet for steps t_now-4 .. t_now-1  <=>  la (= last active step + 1) + 4 <= t_now
-                if ((uint64_t)la + 4ull > (uint64_t)t_now) quiet = false;
-                newest = la > newest ? la : newest;
-            }
-        if ((zt == 0 && has_lo_neighbour) || (zt == (int)nztiles - 1 && has_hi_neighbour)) quiet = false;
-        skip[i] = quiet ? 1 : 0;
-        run += quiet ? 0u : 1u;
-    }
-    for (int o = 16; o > 0; o >>= 1) run += __shfl_xor_sync(0xFFFFFFFFu, run, o);
-    if ((threadIdx.x & 31) == 0 && run) atomicAdd(&stats[0], (unsigned long long)run);
-    if (blockIdx.x == 0 && threadIdx.x == 0) stats[1] = n;
-}
+// ---- settled-tile plan: ONE small kernel per launch of a SKIP step kernel --------------------------------------
+// A tile is *quiet* at step t_now iff it and its 8 neighbours in (z-tile, y-tile) space saw no enabled block during
+// the last four steps (all four offset phases), so nothing in or around it can change now (SCHEDULE.md §4).  Edge
+// z-tiles next to another slab are never quiet (the neighbour's activity is not visible here).
+//
+// The plan kernel turns the tiles' last_active stamps straight into the list of live march segments the SKIP step
+// kernel deals out to its warps (round 1 used a skip-map kernel, a run-list kernel and two memsets per pass):
+// one WARP per pair group looks at its y-tiles 32 at a time (live unless quiet for both rows) and lane 0 emits the
+// runs.  y-block b (BLK iterations) stores tile b's planes except its top LAG + 1, which the first NS iterations of
+// block b + 1 store; so a maximal range of live tiles [Ta, Tb) needs iterations [BLK·Ta, BLK·Tb + NS) — whole blocks
+// plus a short tail.  Ranges are chopped into pieces of `chop` blocks so that every marching warp gets several runs.
+// Order in the list is arbitrary: runs write disjoint planes (what a run stores into neighbouring static tiles is
+// their unchanged content).
+//
+// No memset, no second kernel: the counters rotate.  stats[3][2] = (tiles live, tiles total) of the pass before
+// (read: chop length), of this pass (accumulated) and of the next (zeroed here); nruns[2] likewise per launch.
+struct PlanParams {
+    const uint32_t *last_active;
+    uint32_t nztiles, nytiles, ztile_log2, blk_log2;
+    uint32_t nzl, lz_first, pair_begin, pair_end, groups, nit, ns;
+    uint32_t nw;                          // marching work units of the step kernel that follows
+    uint32_t t_now;
+    int has_lo_neighbour, has_hi_neighbour;
+    int force_live;                       // the grid just came from the host: nothing is known to be static
+    const unsigned long long *stats_prev;
+    unsigned long long *stats_cur, *stats_next;
+    uint32_t *runs, *nruns, *nruns_next;
+};
 
-// The live march segments of one launch, for the SKIP kernels.  One WARP per pair group looks at its
-// y-tiles 32 at a time (a tile is live unless skip_map_kernel proved it static for both rows) and lane 0
-// emits the runs: y-block b (BLK iterations) stores tile b's planes except its top LAG + 1, which the first
-// NS iterations of block b + 1 store.  So a maximal range of live tiles [Ta, Tb) needs iterations
-// [BLK·Ta, BLK·Tb + NS) — whole blocks plus a short tail, not the whole block Tb.  Ranges are chopped into
-// pieces of `chop` blocks so that every marching warp gets several runs.  Order in the list is arbitrary:
-// runs write disjoint planes (what a run stores into neighbouring static tiles is their unchanged content).
-__global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t ztile_log2, uint32_t blk_log2,
-                                 uint32_t nzl, uint32_t lz_first, uint32_t pair_begin, uint32_t pair_end,
-                                 uint32_t groups, uint32_t nit, uint32_t ns, uint32_t nw, const unsigned long long *stats,
-                                 uint32_t *runs, uint32_t *nruns) {
-    const uint32_t npairs = pair_end - pair_begin;
-    const uint32_t npg = (npairs + groups - 1) / groups;
-    const uint32_t blk = 1u << blk_log2;
-    const uint32_t nblk = (nit + blk - 1u) >> blk_log2;
+__global__ void skip_plan_kernel(const PlanParams q) {
+    const uint32_t npairs = q.pair_end - q.pair_begin;
+    const uint32_t npg = (npairs + q.groups - 1) / q.groups;
+    const uint32_t blk = 1u << q.blk_log2;
+    const uint32_t nblk = (q.nit + blk - 1u) >> q.blk_log2;
     const uint32_t lane = threadIdx.x & 31u;
-    // Chop length (1, 2 or 4 blocks) from the live tile fraction of this step: every run re-reads LEAD plane
-    // pairs, so long runs waste least, but the warps must also get equal shares; take the length with
-    // the smallest estimated makespan  ceil(runs / warps) x (iterations per run + lead-in).
-    const unsigned long long live = stats[0], tot = stats[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.stats_next[0] = 0ull;
+        *q.nruns_next = 0u;
+        q.stats_cur[1] = (unsigned long long)q.nztiles * q.nytiles;
+    }
+    // Chop length (1, 2 or 4 blocks) from the live tile fraction of the previous pass: every run re-reads LEAD plane
+    // pairs, so long runs waste least, but the warps must also get equal shares; take the length with the smallest
+    // estimated makespan  ceil(runs / warps) x (iterations per run + lead-in).
+    const unsigned long long live = q.stats_prev[0], tot = q.stats_prev[1];
     const unsigned long long blocks_live = tot ? ((unsigned long long)npg * nblk * live + tot - 1) / tot : (unsigned long long)npg * nblk;
     uint32_t chop = 4u;
     unsigned long long best = ~0ull;
     for (uint32_t c = 4u; c >= 1u; c >>= 1) {
         const unsigned long long nr = (blocks_live + c - 1) / c;
-        const unsigned long long span = ((nr + nw - 1) / (nw ? nw : 1u)) * (unsigned long long)(c * blk + 3u);
+        const unsigned long long span = ((nr + q.nw - 1) / (q.nw ? q.nw : 1u)) * (unsigned long long)(c * blk + 3u);
         if (span < best) { best = span; chop = c; }
     }
-    auto quiet = [&](int32_t oz, uint32_t yt) -> bool {
-        if (oz < 0 || oz >= (int32_t)nzl || yt >= nytiles) return true;
-        return skip[(size_t)((uint32_t)oz >> ztile_log2) * nytiles + yt] != 0;
+    auto tile_quiet = [&](uint32_t zt, uint32_t yt) -> bool {
+        if (q.force_live) return false;
+        if ((zt == 0 && q.has_lo_neighbour) || (zt == q.nztiles - 1 && q.has_hi_neighbour)) return false;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int z = (int)zt + dz, y = (int)yt + dy;
+                if (z < 0 || z >= (int)q.nztiles || y < 0 || y >= (int)q.nytiles) continue;
+                // quiet for steps t_now-4 .. t_now-1  <=>  la (= last active step + 1) + 4 <= t_now
+                if ((uint64_t)q.last_active[(size_t)z * q.nytiles + y] + 4ull > (uint64_t)q.t_now) return false;
+            }
+        return true;
     };
+    const uint32_t zmask = (1u << q.ztile_log2) - 1u;
     const uint32_t wpb = blockDim.x >> 5;
+    uint32_t live_tiles = 0;              // this lane's count of live tiles (each tile is counted by the pair holding its first plane)
     for (uint32_t pg = blockIdx.x * wpb + (threadIdx.x >> 5); pg < npg; pg += gridDim.x * wpb) {
         // live mask of y-tiles [base, base + 32) for the rows of this pair group
-        auto live_mask = [&](uint32_t base) -> uint32_t {
+        auto live_mask = [&](uint32_t base, bool count) -> uint32_t {
             const uint32_t yt = base + lane;
             bool act = false;
             if (yt < nblk) {
-                for (uint32_t g = 0; g < groups; ++g) {
-                    const uint32_t pair = pair_begin + pg * groups + g;
-                    if (pair >= pair_end) break;
-                    const int32_t ozl = (int32_t)(lz_first + 2u * pair) - 1, ozr = ozl + 1;
-                    const bool q0 = quiet(ozl, yt), q1 = quiet(ozr, yt);
-                    act = act || !(q0 & q1);
+                for (uint32_t g = 0; g < q.groups; ++g) {
+                    const uint32_t pair = q.pair_begin + pg * q.groups + g;
+                    if (pair >= q.pair_end) break;
+                    const int32_t ozl = (int32_t)(q.lz_first + 2u * pair) - 1, ozr = ozl + 1;
+                    const bool inl = ozl >= 0 && ozl < (int32_t)q.nzl && yt < q.nytiles;
+                    const bool inr = ozr >= 0 && ozr < (int32_t)q.nzl && yt < q.nytiles;
+                    const uint32_t ztl = inl ? (uint32_t)ozl >> q.ztile_log2 : 0u, ztr = inr ? (uint32_t)ozr >> q.ztile_log2 : 0u;
+                    const bool ql = inl ? tile_quiet(ztl, yt) : true;
+                    const bool qr = inr ? ((inl && ztr == ztl) ? ql : tile_quiet(ztr, yt)) : true;
+                    act = act || !(ql & qr);
+                    if (count) {
+                        if (inl && ((uint32_t)ozl & zmask) == 0u) live_tiles += ql ? 0u : 1u;
+                        if (inr && ((uint32_t)ozr & zmask) == 0u) live_tiles += qr ? 0u : 1u;
+                    }
                 }
             }
             return __ballot_sync(0xFFFFFFFFu, act);
@@ -668,8 +722,8 @@ __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t
             int32_t start = -1;
             for (uint32_t base = 0, wi = 0; base <= nblk; base += 32u, ++wi) {
                 uint32_t mask;
-                if (sweep == 0) { mask = live_mask(base); if (wi < CACHE) cache[wi] = mask; }
-                else mask = wi < CACHE ? cache[wi] : live_mask(base);
+                if (sweep == 0) { mask = live_mask(base, true); if (wi < CACHE) cache[wi] = mask; }
+                else mask = wi < CACHE ? cache[wi] : live_mask(base, false);
                 if (lane == 0) {
                     for (uint32_t k = 0; k < 32u && base + k <= nblk; ++k) {
                         const uint32_t b = base + k;
@@ -678,9 +732,9 @@ __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t
                             if (sweep == 0) {
                                 ++count;
                             } else {
-                                uint32_t e = b << blk_log2;
-                                if (!a) e += ns;                     // the range ends here: tail that stores the last tile's top planes
-                                runs[3u * at] = pg; runs[3u * at + 1u] = (uint32_t)start << blk_log2; runs[3u * at + 2u] = e < nit ? e : nit;
+                                uint32_t e = b << q.blk_log2;
+                                if (!a) e += q.ns;                   // the range ends here: tail that stores the last tile's top planes
+                                q.runs[3u * at] = pg; q.runs[3u * at + 1u] = (uint32_t)start << q.blk_log2; q.runs[3u * at + 2u] = e < q.nit ? e : q.nit;
                                 ++at;
                             }
                             start = -1;
@@ -689,9 +743,11 @@ __global__ void skip_runs_kernel(const uint8_t *skip, uint32_t nytiles, uint32_t
                     }
                 }
             }
-            if (sweep == 0 && lane == 0 && count) at = atomicAdd(nruns, count);
+            if (sweep == 0 && lane == 0 && count) at = atomicAdd(q.nruns, count);
         }
     }
+    for (int o = 16; o > 0; o >>= 1) live_tiles += __shfl_xor_sync(0xFFFFFFFFu, live_tiles, o);
+    if (lane == 0 && live_tiles) atomicAdd(&q.stats_cur[0], (unsigned long long)live_tiles);
 }
 
 }  // namespace fs3d

@@ -191,6 +191,11 @@ class SlabWorld:
     def refresh_halos(self):
         """After generate/upload/set_cell: make the front buffer's ghost planes current."""
         if self.p2p:
+            # A rank's pass k only waits for its neighbours' pass k - 1, so a neighbour may still be running its last
+            # pass — reading the very ghost plane an upload / load (which flip buffers) is about to overwrite.  Every
+            # rank therefore drains its stream and meets the others BEFORE anything is stored into a neighbour.
+            self.engine.sync()
+            dist.barrier(group=self.group)
             self.engine.push_halos()
             dist.barrier(group=self.group)
             self.exchanges += 1
@@ -237,7 +242,9 @@ class SlabWorld:
         w.slab_step_host_begin(host_in)
         dist.barrier(group=self.group)          # every ghost plane holds its neighbour's edge plane
         out = w.slab_step_host(host_in, host_out, n)
-        dist.barrier(group=self.group)          # ghost planes may be overwritten by the next call
+        # No second barrier: the next call's _begin stores into the ghost planes of the buffer this call WROTE
+        # (the library flipped buffers), which no rank reads before it has passed the next call's barrier above —
+        # and a rank only gets there after its own slab_step_host of this call has returned.
         self.step_index += int(n)
         self._halos_stale = True
         return out

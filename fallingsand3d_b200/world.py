@@ -18,6 +18,7 @@ SCENE_EMPTY, SCENE_SAND_BLOCK, SCENE_MIXED, SCENE_RANDOM, SCENE_MIXED_NOISE = 0,
 FLAG_SKIP_SETTLED = 1
 FLAG_NO_FUSE = 2
 FLAG_NO_PEER_PUSH = 4
+FLAG_PEER_PUSH_SHARED_DEVICE = 8
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
@@ -242,6 +243,20 @@ class VoxelWorld:
         lo = C.create_string_buffer(lower_blob, self.IPC_BLOB_BYTES) if lower_blob is not None else None
         hi = C.create_string_buffer(upper_blob, self.IPC_BLOB_BYTES) if upper_blob is not None else None
         _check(self._lib.fs3d_slab_ipc_attach(self._h, lo, hi))
+
+    def push_wait_stats(self):
+        """(ns blocked on neighbours' arrival counters summed over warps, longest single wait ns, blocking waits); resets."""
+        v = (C.c_uint64 * 3)()
+        _check(self._lib.fs3d_push_wait_stats(self._h, v))
+        return int(v[0]), int(v[1]), int(v[2])
+
+    def slab_attach_local(self, lower, upper):
+        """Wire this slab world to the worlds holding the adjacent slabs in the same process (None at the boundary)."""
+        _check(self._lib.fs3d_slab_attach_local(self._h, lower._h if lower is not None else None,
+                                                upper._h if upper is not None else None))
+
+    def frame_attach_local(self, owner, slot):
+        _check(self._lib.fs3d_frame_attach_local(self._h, owner._h, int(slot)))
 
     def slab_step_host_begin(self, grid_in):
         assert grid_in.dtype == np.uint8 and grid_in.flags.c_contiguous and grid_in.shape == self.shape

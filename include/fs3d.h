@@ -61,6 +61,8 @@ extern "C" {
 #define FS3D_FLAG_NO_FUSE       2u   /* one kernel pass per step (default: steps 2k, 2k+1 fuse into one pass) */
 #define FS3D_FLAG_NO_PEER_PUSH  4u   /* n_gpus > 1: exchange halos with peer copies on a side stream instead of
                                         storing them from inside the step kernels (the default with peer access) */
+#define FS3D_FLAG_PEER_PUSH_SHARED_DEVICE 8u /* n_gpus > 1 with several slabs on ONE device: use the fused halo push
+                                        anyway (default there: peer copies).  Lets a one-GPU box run the PUSH kernels. */
 
 /* scene ids for fs3d_generate (SCHEDULE.md §5) */
 #define FS3D_SCENE_EMPTY        0
@@ -198,7 +200,17 @@ int  fs3d_slab_step_finish(fs3d_world *w);
 #define FS3D_IPC_BLOB_BYTES 256
 int  fs3d_slab_ipc_export(fs3d_world *w, void *blob, uint64_t blob_bytes);
 int  fs3d_slab_ipc_attach(fs3d_world *w, const void *lower_blob, const void *upper_blob);
+/* The same wiring between slab worlds of ONE process (one host thread per GPU — or several slabs on one GPU):
+ * plain pointers instead of IPC handles.  lower / upper = the worlds holding the adjacent slabs, NULL at the global
+ * boundary.  Call it on every slab world, then fs3d_slab_push_halos on every one, before the first fs3d_step. */
+int  fs3d_slab_attach_local(fs3d_world *w, fs3d_world *lower, fs3d_world *upper);
 int  fs3d_slab_push_halos(fs3d_world *w);
+/* Cost of inter-GPU skew: ns the PUSH kernels spent blocked on a neighbour's arrival counter since the last call
+ * (out[0] summed over warps, out[1] longest single wait, out[2] number of blocking waits); resets the counters. */
+int  fs3d_push_wait_stats(fs3d_world *w, uint64_t out[3]);
+/* Watchdog: a PUSH kernel that has waited FS3D_PUSH_TIMEOUT_MS (environment, default 20000) for a neighbour's halo
+ * gives up; the next fs3d_sync (or any call that synchronises) returns FS3D_ERR_CUDA naming the stalled side, and the
+ * world refuses to step again (its cells are undefined).  Nothing hangs. */
 
 /* ---- fused multi-rank ray-march (one process per GPU): march + composite over peer memory ----
  * The compositor rank allocates a frame of n_slots x (width x height) 64-bit words and exports it;
@@ -211,6 +223,7 @@ int  fs3d_slab_push_halos(fs3d_world *w);
  * Camera and shading are those of shaders/fs_raymarch.{vert,frag} as for fs3d_raymarch. */
 int  fs3d_frame_export(fs3d_world *w, uint32_t width, uint32_t height, uint32_t n_slots, void *blob, uint64_t blob_bytes);
 int  fs3d_frame_attach(fs3d_world *w, const void *blob, uint32_t slot);
+int  fs3d_frame_attach_local(fs3d_world *w, fs3d_world *owner, uint32_t slot);   /* same, compositor world in this process */
 int  fs3d_raymarch_to_frame(fs3d_world *w, const fs3d_camera *cam, uint32_t mode);   /* asynchronous */
 int  fs3d_frame_resolve(fs3d_world *w, uint8_t *host_rgba8);
 

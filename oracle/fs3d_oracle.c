@@ -67,9 +67,11 @@ static int heavier(uint8_t u, uint8_t l) {
 
 static void swap8(uint8_t *p, uint8_t *q) { uint8_t t = *p; *p = *q; *q = t; }
 
-/* Applies F, D, L to one block.  Returns 1 if the block is "enabled" (something would move
- * with coin = 1), else 0. */
-static int block_rule(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, int coin) {
+/* Applies F, D, L to one block whose upper-left cell `a` is global cell (X, Y, Z).  Returns 1 if the
+ * block is "enabled" (something would move with coin = 1), else 0.  The coin is only drawn when L is
+ * enabled: then a and b are WATER/EMPTY, i.e. both inside the grid, so (X, Y, Z) is in range
+ * (SCHEDULE.md §3 "the coin only matters when both upper cells are inside the grid"). */
+static int block_rule(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, uint32_t key, int64_t X, int64_t Y, int64_t Z) {
     int enabled = 0;
     /* F */
     if (heavier(*a, *c)) { swap8(a, c); enabled = 1; }
@@ -80,7 +82,7 @@ static int block_rule(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, int coin) 
     /* L */
     if ((*a == WATER && *b == EMPTY) || (*b == WATER && *a == EMPTY)) {
         enabled = 1;
-        if (coin) swap8(a, b);
+        if (coin_at(key, X, Y, Z)) swap8(a, b);
     }
     return enabled;
 }
@@ -112,22 +114,38 @@ static int first_origin(int64_t lo, int off) {
     return (int)h0;
 }
 
-/* One XY sub-step on planes z in [zlo, zhi). Returns number of enabled blocks. */
+/* A block through the bounds-checked accessors (cells outside the grid read STONE and are not written). */
+static int block_checked(const grid_t *g, uint32_t key, int64_t xa, int64_t ya, int64_t za, int64_t xb, int64_t zb) {
+    /* a = (xa, ya, za), b = (xb, ya, zb) upper row; c, d the cells below them */
+    uint8_t a = rd(g, xa, ya, za), b = rd(g, xb, ya, zb), c = rd(g, xa, ya - 1, za), d = rd(g, xb, ya - 1, zb);
+    int en = block_rule(&a, &b, &c, &d, key, xa, ya, za);
+    wr(g, xa, ya, za, a); wr(g, xb, ya, zb, b); wr(g, xa, ya - 1, za, c); wr(g, xb, ya - 1, zb, d);
+    return en;
+}
+
+static int held(const grid_t *g, int64_t z) { return z >= 0 && z < g->nzg && z >= g->zbase && z < g->zbase + g->narr; }
+
+/* One XY sub-step on planes z in [zlo, zhi). Returns number of enabled blocks.
+ * Blocks are disjoint, so (plane, block-row) pairs are independent work items: the loop nest is
+ * collapsed over both so that a thin slab sample still feeds every host thread.  Blocks that lie
+ * wholly inside the held planes take the direct-pointer path; the rest go through rd()/wr(). */
 static int64_t substep_xy(const grid_t *g, uint32_t key, int ox, int oy, int64_t zlo, int64_t zhi) {
     int64_t enabled = 0;
-    int64_t z;
-#pragma omp parallel for reduction(+ : enabled) schedule(static)
+    const int64_t ystart = first_origin(0, oy), xstart = first_origin(0, ox);
+    const int64_t nyb = (g->ny - ystart + 1) / 2;   /* y0 = ystart + 2 yb < ny */
+    int64_t z, yb;
+#pragma omp parallel for collapse(2) reduction(+ : enabled) schedule(static)
     for (z = zlo; z < zhi; ++z) {
-        for (int64_t y0 = first_origin(0, oy); y0 < g->ny; y0 += 2) {
-            for (int64_t x0 = first_origin(0, ox); x0 < g->nx; x0 += 2) {
-                uint8_t a = rd(g, x0, y0 + 1, z), b = rd(g, x0 + 1, y0 + 1, z);
-                uint8_t c = rd(g, x0, y0, z),     d = rd(g, x0 + 1, y0, z);
-                int coin = 0;
-                if (x0 >= 0 && x0 + 1 < g->nx && y0 + 1 < g->ny) coin = coin_at(key, x0, y0 + 1, z);
-                enabled += block_rule(&a, &b, &c, &d, coin);
-                wr(g, x0, y0 + 1, z, a); wr(g, x0 + 1, y0 + 1, z, b);
-                wr(g, x0, y0, z, c);     wr(g, x0 + 1, y0, z, d);
+        for (yb = 0; yb < nyb; ++yb) {
+            const int64_t y0 = ystart + 2 * yb;
+            int64_t x0 = xstart;
+            if (y0 >= 0 && y0 + 1 < g->ny && held(g, z)) {
+                uint8_t *lo = g->arr + g->nx * (y0 + g->ny * (z - g->zbase)), *up = lo + g->nx;
+                if (x0 < 0) { enabled += block_checked(g, key, x0, y0 + 1, z, x0 + 1, z); x0 += 2; }
+                for (; x0 + 1 < g->nx; x0 += 2)
+                    enabled += block_rule(up + x0, up + x0 + 1, lo + x0, lo + x0 + 1, key, x0, y0 + 1, z);
             }
+            for (; x0 < g->nx; x0 += 2) enabled += block_checked(g, key, x0, y0 + 1, z, x0 + 1, z);
         }
     }
     return enabled;
@@ -136,21 +154,21 @@ static int64_t substep_xy(const grid_t *g, uint32_t key, int ox, int oy, int64_t
 /* One ZY sub-step over the blocks that intersect global planes [zlo, zhi). */
 static int64_t substep_zy(const grid_t *g, uint32_t key, int oz, int oy, int64_t zlo, int64_t zhi) {
     int64_t enabled = 0;
-    int64_t zstart = first_origin(zlo, oz);
-    int64_t nblk = (zhi - zstart + 1) / 2; /* z0 = zstart + 2k < zhi */
-    int64_t k;
-#pragma omp parallel for reduction(+ : enabled) schedule(static)
+    const int64_t zstart = first_origin(zlo, oz), ystart = first_origin(0, oy);
+    const int64_t nblk = (zhi - zstart + 1) / 2; /* z0 = zstart + 2k < zhi */
+    const int64_t nyb = (g->ny - ystart + 1) / 2;
+    int64_t k, yb;
+#pragma omp parallel for collapse(2) reduction(+ : enabled) schedule(static)
     for (k = 0; k < nblk; ++k) {
-        int64_t z0 = zstart + 2 * k;
-        for (int64_t y0 = first_origin(0, oy); y0 < g->ny; y0 += 2) {
-            for (int64_t x = 0; x < g->nx; ++x) {
-                uint8_t a = rd(g, x, y0 + 1, z0), b = rd(g, x, y0 + 1, z0 + 1);
-                uint8_t c = rd(g, x, y0, z0),     d = rd(g, x, y0, z0 + 1);
-                int coin = 0;
-                if (z0 >= 0 && z0 + 1 < g->nzg && y0 + 1 < g->ny) coin = coin_at(key, x, y0 + 1, z0);
-                enabled += block_rule(&a, &b, &c, &d, coin);
-                wr(g, x, y0 + 1, z0, a); wr(g, x, y0 + 1, z0 + 1, b);
-                wr(g, x, y0, z0, c);     wr(g, x, y0, z0 + 1, d);
+        for (yb = 0; yb < nyb; ++yb) {
+            const int64_t z0 = zstart + 2 * k, y0 = ystart + 2 * yb;
+            if (y0 >= 0 && y0 + 1 < g->ny && held(g, z0) && held(g, z0 + 1)) {
+                uint8_t *lo0 = g->arr + g->nx * (y0 + g->ny * (z0 - g->zbase)), *up0 = lo0 + g->nx;
+                uint8_t *lo1 = lo0 + g->nx * g->ny, *up1 = lo1 + g->nx;
+                for (int64_t x = 0; x < g->nx; ++x)
+                    enabled += block_rule(up0 + x, up1 + x, lo0 + x, lo1 + x, key, x, y0 + 1, z0);
+            } else {
+                for (int64_t x = 0; x < g->nx; ++x) enabled += block_checked(g, key, x, y0 + 1, z0, x, z0 + 1);
             }
         }
     }
@@ -270,3 +288,19 @@ uint64_t fs3d_oracle_digest(const uint8_t *grid, int64_t nx, int64_t ny, int64_t
 }
 
 int fs3d_oracle_schedule_version(void) { return 1; }
+
+/* host threads the parallel loops above actually get (1 without OpenMP) */
+#ifdef _OPENMP
+#include <omp.h>
+int fs3d_oracle_threads(void) {
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+}
+#else
+int fs3d_oracle_threads(void) { return 1; }
+#endif

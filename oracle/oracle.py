@@ -84,6 +84,7 @@ def lib():
         L.fs3d_oracle_digest.restype = u64
         L.fs3d_oracle_digest.argtypes = [u8p, i64, i64, i64, i64]
         L.fs3d_oracle_schedule_version.restype = C.c_int
+        L.fs3d_oracle_threads.restype = C.c_int
         L.fs3d_sweep_step.restype = i64
         L.fs3d_sweep_step.argtypes = [u8p, i64, i64, i64, C.c_int, u64]
         L.fs3d_oracle_raymarch.restype = None
@@ -145,6 +146,11 @@ def digest(grid, zlo=0):
 def sweep_step(grid, with_lateral=0, parity=0):
     nz, ny, nx = _chk(grid)
     return lib().fs3d_sweep_step(_ptr(grid), nx, ny, nz, with_lateral, parity)
+
+
+def threads():
+    """Host threads the oracle's OpenMP loops actually run on (honours OMP_NUM_THREADS and the affinity mask)."""
+    return int(lib().fs3d_oracle_threads())
 
 
 def key(seed, t, axis):

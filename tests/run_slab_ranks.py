@@ -130,6 +130,32 @@ def main():
         ok = bool(flag.item())
         if not ok:
             break
+    # step -> upload -> step with one rank's GPU deliberately late: a pass only waits for the neighbours'
+    # previous pass, so refresh_halos must drain and barrier BEFORE it stores into a neighbour's ghost plane
+    if ok:
+        nx, ny, nz = 256, 64, 24
+        sw = SlabWorld(nx, ny, nz, seed=13, p2p=True)
+        with fs3d.VoxelWorld(nx, ny, nz, seed=13) as ref:
+            sw.generate(fs3d.SCENE_MIXED_NOISE, 4)
+            ref.generate(fs3d.SCENE_MIXED_NOISE, 4)
+            sw.step(2)
+            if rank == dist.get_world_size() - 1:
+                with torch.cuda.stream(sw.engine.stream):
+                    torch.cuda._sleep(1_500_000_000)          # ~0.75 s of GPU time in front of this rank's next pass
+            sw.step(2)
+            ref.step(4)
+            other = np.ascontiguousarray(ref.download()[::-1, :, ::-1])       # some other valid grid
+            sw.upload(np.ascontiguousarray(other[sw.z_begin:sw.z_end]))
+            ref.upload(other)
+            sw.step(6)
+            ref.step(6)
+            if not np.array_equal(sw.download(), ref.download()[sw.z_begin:sw.z_end]):
+                ok = False
+                print(f"MISMATCH after step / upload / step with a delayed rank (rank {rank})", flush=True)
+        sw.close()
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
     if rank == 0:
         print("SLAB_NCCL_OK" if ok else "SLAB_NCCL_FAIL", flush=True)
     dist.barrier()

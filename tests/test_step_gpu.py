@@ -255,3 +255,41 @@ def test_full_extent_planes_match_oracle(fs3d, oracle, dims, steps):
     # full BASELINE x and y extents (every word position of a row, every march segment shape), few planes in z
     nx, ny, nz = dims
     run_and_compare(fs3d, oracle, nx, ny, nz, scene=4, seed=2, steps=steps, every=steps)
+
+
+def test_headline_grid_2048_equals_oracle_cell_for_cell(fs3d, oracle):
+    # north_star: "a 2048^3 mixed sand/water scene stepping bit-exact to the schedule reference".  The FULL headline
+    # grid (bench.py's workload: MIXED_NOISE, scene seed 1, coin seed 1), two fused passes = 4 steps, every one of the
+    # 8.6 G cells compared with the CPU oracle run on the host (8 GiB per array; ~10 s of oracle time on the box).
+    n = 2048
+    g = oracle.generate(n, n, n, 4, 1)
+    with fs3d.VoxelWorld(n, n, n, seed=1) as w:
+        w.generate(fs3d.SCENE_MIXED_NOISE, 1)
+        assert w.digest() == oracle.digest(g)
+        w.step(4)
+        oracle.run(g, 1, 0, 4)
+        got = w.download()
+        assert w.digest() == oracle.digest(g)
+    same = np.array_equal(got, g)
+    if not same:
+        bad = np.argwhere(got != g)
+        raise AssertionError(f"2048^3: {len(bad)} cells differ after 4 steps, first (z,y,x)={bad[0].tolist()}")
+
+
+def test_headline_grid_matches_oracle_digests(fs3d):
+    # tests/golden/bench_digests.json: digests of the full 2048^3 bench workload computed by the CPU oracle (generator
+    # beside it) at the step counts bench.py ends on; the GPU must reproduce every one, fused and unfused
+    with open(os.path.join(GOLDEN, "bench_digests.json")) as f:
+        gold = json.load(f)
+    nx, ny, nz = gold["dims"]
+    steps = sorted(int(k) for k in gold["digests"])
+    for flags in (0, fs3d.FLAG_NO_FUSE):
+        with fs3d.VoxelWorld(nx, ny, nz, seed=gold["seed"], flags=flags) as w:
+            w.generate(gold["scene"], gold["scene_seed"])
+            assert w.digest() == int(gold["digest0"], 16)
+            t = 0
+            for upto in steps:
+                w.step(upto - t)
+                t = upto
+                assert w.digest() == int(gold["digests"][str(upto)], 16), f"step {upto} flags {flags}"
+            assert [int(v) for v in w.histogram()[:4]] == gold["histogram"]
