@@ -75,7 +75,7 @@ struct Slab {
     } frame;
     // settled-tile skipping
     uint32_t *d_last_active = nullptr;         // non-null <=> FS3D_FLAG_SKIP_SETTLED
-    unsigned long long *d_stats = nullptr;     // [3][2] (tiles live, tiles total), rotating per pass (skip_plan_kernel)
+    unsigned long long *d_stats = nullptr;     // [3][4] (tiles live, tiles total, live ranges, live iterations), rotating per pass (skip_plan_kernel)
     uint32_t *d_runs = nullptr, *d_nruns = nullptr;   // live march segments of the launch in flight; nruns[2] rotates per launch
     uint64_t plan_pass = 0, plan_launch = 0;   // passes / SKIP launches planned so far (indices of the rotating counters)
     uint32_t nztiles = 0, nytiles = 0;
@@ -184,12 +184,15 @@ static int init_slab(fs3d_world *w, Slab &s) {
         s.nytiles = (w->desc.ny + (1u << YTILE_LOG2) - 1) >> YTILE_LOG2;
         const size_t nt = (size_t)s.nztiles * s.nytiles;
         FS3D_CUDA(cudaMalloc(&s.d_last_active, nt * sizeof(uint32_t)));
-        FS3D_CUDA(cudaMalloc(&s.d_stats, 6 * sizeof(unsigned long long)));
-        const size_t max_runs = ((size_t)s.nzl / 2 + 2) * (((size_t)w->desc.ny / 2 + 2) / (1u << (YTILE_LOG2 - 1)) + 2);
+        FS3D_CUDA(cudaMalloc(&s.d_stats, 12 * sizeof(unsigned long long)));
+        // runs are pieces of >= 4 iterations (skip_plan_kernel: piece length >= 8 before the equal split), at most one
+        // range per two y-blocks
+        const size_t its = (size_t)w->desc.ny / 2 + 2;
+        const size_t max_runs = ((size_t)s.nzl / 2 + 2) * (its / 4 + its / (1u << YTILE_LOG2) + 4);
         FS3D_CUDA(cudaMalloc(&s.d_runs, max_runs * 3 * sizeof(uint32_t)));
         FS3D_CUDA(cudaMalloc(&s.d_nruns, 2 * sizeof(uint32_t)));
         FS3D_CUDA(cudaMemsetAsync(s.d_last_active, 0, nt * sizeof(uint32_t), s.s_main));
-        FS3D_CUDA(cudaMemsetAsync(s.d_stats, 0, 6 * sizeof(unsigned long long), s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_stats, 0, 12 * sizeof(unsigned long long), s.s_main));
         FS3D_CUDA(cudaMemsetAsync(s.d_nruns, 0, 2 * sizeof(uint32_t), s.s_main));
     }
     // both buffers start as EMPTY with STONE ghost planes (closed box / not-yet-exchanged halo)
@@ -328,7 +331,7 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
         q.has_lo_neighbour = s.z0 > 0; q.has_hi_neighbour = s.z0 + s.nzl < w->desc.nz;
         q.force_live = w->force_live ? 1 : 0;
         const uint64_t k = s.plan_pass;           // begin_skip_pass advanced it for this pass
-        q.stats_prev = s.d_stats + 2 * ((k + 2) % 3); q.stats_cur = s.d_stats + 2 * (k % 3); q.stats_next = s.d_stats + 2 * ((k + 1) % 3);
+        q.stats_prev = s.d_stats + 4 * ((k + 2) % 3); q.stats_cur = s.d_stats + 4 * (k % 3); q.stats_next = s.d_stats + 4 * ((k + 1) % 3);
         q.runs = s.d_runs; q.nruns = s.d_nruns + (s.plan_launch & 1); q.nruns_next = s.d_nruns + ((s.plan_launch + 1) & 1);
         s.plan_launch++;
         skip_plan_kernel<<<(unsigned)((npg + 3) / 4), 128, 0, s.s_main>>>(q);
@@ -997,7 +1000,7 @@ int fs3d_histogram(fs3d_world *w, uint64_t counts[256]) {
     const size_t pb = plane_bytes(w);
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
-        FS3D_CUDA(cudaMemsetAsync(s.d_scratch, 0, 256 * sizeof(unsigned long long), s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_scratch, 0, 2512 * sizeof(unsigned long long), s.s_main));
         uint64_t n16 = pb * s.nzl / 16;
         histogram_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), n16, s.d_scratch);
         FS3D_CUDA(cudaGetLastError());
@@ -1040,7 +1043,7 @@ int fs3d_activity(fs3d_world *w, uint64_t *tiles_run, uint64_t *tiles_total) {
         if (!s.d_last_active) { *tiles_run += 1; *tiles_total += 1; continue; }   // skipping off: everything runs
         FS3D_CUDA(cudaSetDevice(s.device));
         unsigned long long st[2] = {0, 0};
-        FS3D_CUDA(cudaMemcpy(st, s.d_stats + 2 * (s.plan_pass % 3), sizeof(st), cudaMemcpyDeviceToHost));
+        FS3D_CUDA(cudaMemcpy(st, s.d_stats + 4 * (s.plan_pass % 3), sizeof(st), cudaMemcpyDeviceToHost));
         *tiles_run += st[0];
         *tiles_total += st[1] ? st[1] : (unsigned long long)s.nztiles * s.nytiles;
     }

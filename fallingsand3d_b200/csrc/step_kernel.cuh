@@ -636,8 +636,9 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
 // Order in the list is arbitrary: runs write disjoint planes (what a run stores into neighbouring static tiles is
 // their unchanged content).
 //
-// No memset, no second kernel: the counters rotate.  stats[3][2] = (tiles live, tiles total) of the pass before
-// (read: chop length), of this pass (accumulated) and of the next (zeroed here); nruns[2] likewise per launch.
+// No memset, no second kernel: the counters rotate.  stats[3][4] = (tiles live, tiles total, live ranges, live
+// iterations) of the pass before (read: piece length), of this pass (accumulated) and of the next (zeroed here);
+// nruns[2] likewise per launch.
 struct PlanParams {
     const uint32_t *last_active;
     uint32_t nztiles, nytiles, ztile_log2, blk_log2;
@@ -658,21 +659,28 @@ __global__ void skip_plan_kernel(const PlanParams q) {
     const uint32_t nblk = (q.nit + blk - 1u) >> q.blk_log2;
     const uint32_t lane = threadIdx.x & 31u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.stats_next[0] = 0ull;
+        q.stats_next[0] = 0ull; q.stats_next[2] = 0ull; q.stats_next[3] = 0ull;
         *q.nruns_next = 0u;
         q.stats_cur[1] = (unsigned long long)q.nztiles * q.nytiles;
     }
-    // Chop length (1, 2 or 4 blocks) from the live tile fraction of the previous pass: every run re-reads LEAD plane
-    // pairs, so long runs waste least, but the warps must also get equal shares; take the length with the smallest
-    // estimated makespan  ceil(runs / warps) x (iterations per run + lead-in).
-    const unsigned long long live = q.stats_prev[0], tot = q.stats_prev[1];
-    const unsigned long long blocks_live = tot ? ((unsigned long long)npg * nblk * live + tot - 1) / tot : (unsigned long long)npg * nblk;
-    uint32_t chop = 4u;
-    unsigned long long best = ~0ull;
-    for (uint32_t c = 4u; c >= 1u; c >>= 1) {
-        const unsigned long long nr = (blocks_live + c - 1) / c;
-        const unsigned long long span = ((nr + q.nw - 1) / (q.nw ? q.nw : 1u)) * (unsigned long long)(c * blk + 3u);
-        if (span < best) { best = span; chop = c; }
+    // Piece length.  A maximal range of live tiles of one pair group is cut into equal pieces, one run each.  Every
+    // run re-reads LEAD plane pairs, so long pieces waste least — but in a sparse phase a pass is latency-bound per
+    // warp, not bandwidth-bound, and what counts is that the marching warps get equal shares in as few rounds as
+    // possible.  From the previous pass's ranges and live iterations: take the number of pieces per (mean) range with
+    // the smallest estimated makespan  ceil(runs / warps) x (piece + lead-in).
+    const unsigned long long ranges_prev = q.stats_prev[2], iters_prev = q.stats_prev[3];
+    uint32_t chop_it = 64u;
+    if (ranges_prev) {
+        const unsigned long long mean = (iters_prev + ranges_prev - 1) / ranges_prev;
+        unsigned long long best = ~0ull;
+        for (uint32_t pcs = 1u; pcs <= 16u; ++pcs) {
+            const unsigned long long piece = (mean + pcs - 1) / pcs;
+            if (piece < 8u && pcs > 1u) break;                       // lead-in would dominate
+            const unsigned long long nr = ranges_prev * pcs;
+            const unsigned long long span = ((nr + q.nw - 1) / (q.nw ? q.nw : 1u)) * (piece + 3u);
+            if (best == ~0ull || span * 20ull < best * 19ull) { best = span; chop_it = (uint32_t)piece; }   // shorter pieces must win by > 5 %
+        }
+        if (chop_it < 8u) chop_it = 8u;
     }
     auto tile_quiet = [&](uint32_t zt, uint32_t yt) -> bool {
         if (q.force_live) return false;
@@ -689,6 +697,8 @@ __global__ void skip_plan_kernel(const PlanParams q) {
     const uint32_t zmask = (1u << q.ztile_log2) - 1u;
     const uint32_t wpb = blockDim.x >> 5;
     uint32_t live_tiles = 0;              // this lane's count of live tiles (each tile is counted by the pair holding its first plane)
+    uint32_t my_ranges = 0;               // lane 0: live ranges and live iterations of this warp's pair groups
+    unsigned long long my_iters = 0;
     for (uint32_t pg = blockIdx.x * wpb + (threadIdx.x >> 5); pg < npg; pg += gridDim.x * wpb) {
         // live mask of y-tiles [base, base + 32) for the rows of this pair group
         auto live_mask = [&](uint32_t base, bool count) -> uint32_t {
@@ -728,14 +738,23 @@ __global__ void skip_plan_kernel(const PlanParams q) {
                     for (uint32_t k = 0; k < 32u && base + k <= nblk; ++k) {
                         const uint32_t b = base + k;
                         const bool a = (mask >> k) & 1u;           // tile b live (never for b >= nblk)
-                        if (start >= 0 && (!a || b - (uint32_t)start == chop)) {
+                        if (start >= 0 && !a) {
+                            // live tiles [start, b): iterations [BLK·start, BLK·b + NS) — the tail stores the last tile's top planes
+                            const uint32_t it_a = (uint32_t)start << q.blk_log2;
+                            uint32_t it_e = (b << q.blk_log2) + q.ns;
+                            if (it_e > q.nit) it_e = q.nit;
+                            const uint32_t len = it_e - it_a;
+                            const uint32_t pcs = (len + chop_it - 1u) / chop_it;
+                            const uint32_t plen = (len + pcs - 1u) / pcs;
                             if (sweep == 0) {
-                                ++count;
+                                count += pcs; ++my_ranges; my_iters += len;
                             } else {
-                                uint32_t e = b << q.blk_log2;
-                                if (!a) e += q.ns;                   // the range ends here: tail that stores the last tile's top planes
-                                q.runs[3u * at] = pg; q.runs[3u * at + 1u] = (uint32_t)start << q.blk_log2; q.runs[3u * at + 2u] = e < q.nit ? e : q.nit;
-                                ++at;
+                                for (uint32_t i = 0; i < pcs; ++i) {
+                                    const uint32_t ra = it_a + i * plen, rb = ra + plen < it_e ? ra + plen : it_e;
+                                    if (ra >= rb) break;
+                                    q.runs[3u * at] = pg; q.runs[3u * at + 1u] = ra; q.runs[3u * at + 2u] = rb;
+                                    ++at;
+                                }
                             }
                             start = -1;
                         }
@@ -746,6 +765,7 @@ __global__ void skip_plan_kernel(const PlanParams q) {
             if (sweep == 0 && lane == 0 && count) at = atomicAdd(q.nruns, count);
         }
     }
+    if (lane == 0 && my_ranges) { atomicAdd(&q.stats_cur[2], (unsigned long long)my_ranges); atomicAdd(&q.stats_cur[3], my_iters); }
     for (int o = 16; o > 0; o >>= 1) live_tiles += __shfl_xor_sync(0xFFFFFFFFu, live_tiles, o);
     if (lane == 0 && live_tiles) atomicAdd(&q.stats_cur[0], (unsigned long long)live_tiles);
 }

@@ -23,6 +23,14 @@ static int heavier(uint8_t u, uint8_t l) {
     return density(u) > density(l);
 }
 
+/* first direction tried by cell (x, y, z) in sweep `parity`: a small integer hash, so that a lone liquid cell on a full
+ * layer performs a random walk (and finds the last hole) instead of orbiting on a fixed cycle */
+static int first_dir(int64_t x, int64_t y, int64_t z, uint64_t parity) {
+    uint32_t v = (uint32_t)x * 0x9E3779B1u + (uint32_t)y * 0x85EBCA77u + (uint32_t)z * 0xC2B2AE3Du + (uint32_t)parity * 0x27D4EB2Fu;
+    v ^= v >> 15; v *= 0x2C1B3C6Du; v ^= v >> 12;
+    return (int)(v & 3u);
+}
+
 /* One in-place sweep, y ascending (bottom-up), then z, then x.  Returns the number of moves. */
 int64_t fs3d_sweep_step(uint8_t *g, int64_t nx, int64_t ny, int64_t nz, int with_lateral, uint64_t parity) {
 #define AT(x, y, z) g[(x) + nx * ((y) + ny * (z))]
@@ -38,8 +46,9 @@ int64_t fs3d_sweep_step(uint8_t *g, int64_t nx, int64_t ny, int64_t nz, int with
                     uint8_t t = AT(x, y - 1, z); AT(x, y - 1, z) = m; AT(x, y, z) = t; ++moves; continue;
                 }
                 int moved = 0;
+                const int d0 = first_dir(x, y, z, parity);
                 for (int k = 0; k < 4 && !moved; ++k) {
-                    int dir = (int)((k + parity + (uint64_t)x + (uint64_t)z) & 3);
+                    int dir = (k + d0) & 3;
                     int64_t xs = x + DX[dir], zs = z + DZ[dir];
                     if (y == 0 || !INB(xs, y, zs)) continue;
                     if (AT(xs, y, zs) == STONE) continue;
@@ -49,7 +58,7 @@ int64_t fs3d_sweep_step(uint8_t *g, int64_t nx, int64_t ny, int64_t nz, int with
                 }
                 if (moved || !with_lateral || m != WATER) continue;
                 for (int k = 0; k < 4 && !moved; ++k) {
-                    int dir = (int)((k + parity + (uint64_t)x + (uint64_t)z) & 3);
+                    int dir = (k + d0) & 3;
                     int64_t xs = x + DX[dir], zs = z + DZ[dir];
                     if (!INB(xs, y, zs)) continue;
                     if (AT(xs, y, zs) == EMPTY) { AT(xs, y, zs) = m; AT(x, y, z) = EMPTY; ++moves; moved = 1; }

@@ -176,3 +176,51 @@ def test_settled_state_is_fixed_point_of_standin_sweep(oracle):
     for i in range(50):
         oracle.sweep_step(s, with_lateral=1, parity=i)
     assert np.array_equal(oracle.histogram(s), h0)
+
+
+# ---- settled configurations on deterministic (tie-free) scenes: schedule == stand-in sweep == closed form ----------
+from tests.settle_scenes import basin_scene, settle_closed_form, shaft_scene  # noqa: E402
+
+
+def run_schedule_until_quiet(oracle, g, seed, limit):
+    t = quiet = 0
+    while quiet < 4 and t < limit:
+        quiet = quiet + 1 if oracle.step(g, seed, t) == 0 else 0
+        t += 1
+    assert quiet == 4, f"not settled after {limit} steps"
+    return t
+
+
+def run_sweep_until_quiet(oracle, g, with_lateral, limit):
+    for i in range(limit):
+        if oracle.sweep_step(g, with_lateral=with_lateral, parity=i) == 0:
+            return i
+    raise AssertionError(f"sweep not settled after {limit} sweeps")
+
+
+def test_settled_shafts_equal_standin_sweep_and_closed_form(oracle):
+    # north_star: "reach the same settled configurations as the [stand-in] sweep on deterministic scenes": MIXED
+    # materials (stone + sand + water), tie-free by construction
+    g0 = shaft_scene()
+    want = settle_closed_form(g0)
+    a, b = g0.copy(), g0.copy()
+    run_schedule_until_quiet(oracle, a, seed=7, limit=600)
+    run_sweep_until_quiet(oracle, b, with_lateral=1, limit=600)
+    assert np.array_equal(a, want), "partitioned schedule: shafts not density-sorted"
+    assert np.array_equal(b, want), "stand-in sweep: shafts not density-sorted"
+    # and the seed (coins) cannot matter on a tie-free scene
+    c = g0.copy()
+    run_schedule_until_quiet(oracle, c, seed=12345, limit=600)
+    assert np.array_equal(c, want)
+
+
+def test_settled_basin_equals_standin_sweep(oracle):
+    g0 = basin_scene()
+    want = np.zeros_like(g0)
+    want[:, 0, :] = X
+    want[:, 1:4, :] = W
+    a, b = g0.copy(), g0.copy()
+    run_schedule_until_quiet(oracle, a, seed=3, limit=20000)
+    run_sweep_until_quiet(oracle, b, with_lateral=1, limit=20000)
+    assert np.array_equal(a, want), "partitioned schedule: pool not flat"
+    assert np.array_equal(b, want), "stand-in sweep: pool not flat"

@@ -293,3 +293,33 @@ def test_headline_grid_matches_oracle_digests(fs3d):
                 t = upto
                 assert w.digest() == int(gold["digests"][str(upto)], 16), f"step {upto} flags {flags}"
             assert [int(v) for v in w.histogram()[:4]] == gold["histogram"]
+
+
+def test_gpu_settles_tie_free_scenes_like_the_sweep(fs3d, oracle):
+    # north_star: "reach the same settled configurations as the [stand-in] sweep on deterministic scenes".
+    # With settled-tile skipping on, activity() == 0 is the GPU's own statement that nothing can move any more.
+    from tests.settle_scenes import basin_scene, settle_closed_form, shaft_scene
+    for name, g0, want, limit in (("shafts", shaft_scene(), None, 800), ("basin", basin_scene(), None, 40000)):
+        if name == "shafts":
+            want = settle_closed_form(g0)
+        else:
+            want = np.zeros_like(g0)
+            want[:, 0, :] = X
+            want[:, 1:4, :] = W
+        nz, ny, nx = g0.shape
+        sweep = g0.copy()
+        for i in range(limit):
+            if oracle.sweep_step(sweep, with_lateral=1, parity=i) == 0:
+                break
+        assert np.array_equal(sweep, want), name
+        with fs3d.VoxelWorld(nx, ny, nz, seed=7, flags=fs3d.FLAG_SKIP_SETTLED) as w:
+            w.upload(g0)
+            t = 0
+            while t < limit:
+                w.step(20)
+                t += 20
+                if w.activity()[0] == 0:
+                    break
+            assert w.activity()[0] == 0, f"{name}: GPU world not settled after {t} steps"
+            got = w.download()
+        assert np.array_equal(got, want), f"{name}: GPU settled state differs from the sweep's / the closed form"
