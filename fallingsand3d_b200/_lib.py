@@ -23,6 +23,12 @@ class View(C.Structure):
                 ("step", C.c_uint64)]
 
 
+class Export(C.Structure):
+    _fields_ = [("fd", C.c_int32 * 2), ("alloc_bytes", C.c_uint64), ("first_cell_offset", C.c_uint64), ("front", C.c_uint32),
+                ("device", C.c_int32), ("nx", C.c_uint32), ("ny", C.c_uint32), ("z0", C.c_uint32), ("z1", C.c_uint32),
+                ("pitch_y", C.c_uint64), ("pitch_z", C.c_uint64), ("step", C.c_uint64)]
+
+
 class Camera(C.Structure):
     _fields_ = [("pos", C.c_float * 3), ("yaw_deg", C.c_float), ("aspect", C.c_float)]
 
@@ -57,6 +63,7 @@ SIGNATURES = {
     "fs3d_activity": (C.c_int, [_W, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fs3d_num_slabs": (C.c_int, [_W, C.POINTER(C.c_int32)]),
     "fs3d_volume_view": (C.c_int, [_W, C.c_int32, C.POINTER(View)]),
+    "fs3d_volume_export_fd": (C.c_int, [_W, C.c_int32, C.POINTER(Export)]),
     "fs3d_set_palette": (C.c_int, [_W, C.POINTER(C.c_float)]),
     "fs3d_raymarch": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "fs3d_raymarch_depth": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),

@@ -13,6 +13,10 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>      // driver-API TYPES only: the functions come from cudaGetDriverEntryPoint, so libfs3d.so has no
+                       // link-time dependency on libcuda (it must load on a box without a driver and fail in fs3d_create)
+#include <unistd.h>
+
 #include "common.cuh"
 #include "aux_kernels.cuh"
 #include "step_kernel.cuh"
@@ -43,6 +47,10 @@ struct Slab {
     uint32_t z0 = 0, nzl = 0;         // global planes [z0, z0 + nzl)
     uint8_t *buf[2] = {nullptr, nullptr};   // (nzl + 2) planes each; plane 0 / nzl+1 are ghosts
     size_t bytes = 0;
+    // FS3D_FLAG_EXPORTABLE: the two buffers are driver VMM allocations that can be exported as POSIX file descriptors
+    bool vmm = false;
+    unsigned long long vmm_handle[2] = {0, 0};   // CUmemGenericAllocationHandle
+    size_t vmm_size = 0;                          // mapped size (bytes rounded up to the allocation granularity)
     cudaStream_t s_main = nullptr, s_comm = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_done = nullptr;
     cudaEvent_t ev_out_lo = nullptr, ev_out_hi = nullptr;   // my edge plane has landed in the lower / upper neighbour's ghost
@@ -151,11 +159,107 @@ static int check_dims(const fs3d_desc *d) {
     return FS3D_OK;
 }
 
+// ---- exportable volume memory: driver virtual-memory-management allocations ----------------
+struct DriverApi {
+    CUresult (*memGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*memCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*memAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*memMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*memSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*memUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*memAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*memRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*memExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    bool ok = false;
+};
+static const DriverApi &driver_api() {
+    static DriverApi api = [] {
+        DriverApi a;
+        bool ok = true;
+        auto get = [&](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult st;
+            if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !*fn) ok = false;
+        };
+        get("cuMemGetAllocationGranularity", (void **)&a.memGetAllocationGranularity);
+        get("cuMemCreate", (void **)&a.memCreate);
+        get("cuMemAddressReserve", (void **)&a.memAddressReserve);
+        get("cuMemMap", (void **)&a.memMap);
+        get("cuMemSetAccess", (void **)&a.memSetAccess);
+        get("cuMemUnmap", (void **)&a.memUnmap);
+        get("cuMemAddressFree", (void **)&a.memAddressFree);
+        get("cuMemRelease", (void **)&a.memRelease);
+        get("cuMemExportToShareableHandle", (void **)&a.memExportToShareableHandle);
+        cudaGetLastError();
+        a.ok = ok;
+        return a;
+    }();
+    return api;
+}
+#define FS3D_CU(expr)                                                                                   \
+    do {                                                                                                \
+        CUresult _r = (expr);                                                                           \
+        if (_r != CUDA_SUCCESS)                                                                         \
+            return ::fs3d::fail(_r == CUDA_ERROR_OUT_OF_MEMORY ? FS3D_ERR_OOM : FS3D_ERR_CUDA,          \
+                                std::string(#expr) + ": CUresult " + std::to_string((int)_r));          \
+    } while (0)
+
+static int vmm_alloc(fs3d_world *w, Slab &s, int b) {
+    const DriverApi &d = driver_api();
+    if (!d.ok) return fail(FS3D_ERR_UNSUPPORTED, "FS3D_FLAG_EXPORTABLE: the driver's virtual memory management API is not available");
+    FS3D_CUDA(cudaFree(nullptr));                       // make sure this device's primary context exists and is current
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = s.device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    FS3D_CU(d.memGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM));
+    s.vmm_size = (s.bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h = 0;
+    FS3D_CU(d.memCreate(&h, s.vmm_size, &prop, 0));
+    CUdeviceptr ptr = 0;
+    CUresult r = d.memAddressReserve(&ptr, s.vmm_size, 0, 0, 0);
+    if (r == CUDA_SUCCESS) r = d.memMap(ptr, s.vmm_size, 0, h, 0);
+    if (r == CUDA_SUCCESS) {
+        // readable and writable from every device of this world (peer pushes, the compositor's ray-march)
+        std::vector<CUmemAccessDesc> acc;
+        for (int32_t dev : w->devices) {
+            bool seen = false;
+            for (auto &a : acc) seen = seen || a.location.id == dev;
+            if (seen) continue;
+            CUmemAccessDesc a{};
+            a.location.type = CU_MEM_LOCATION_TYPE_DEVICE; a.location.id = dev; a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+            acc.push_back(a);
+        }
+        r = d.memSetAccess(ptr, s.vmm_size, acc.data(), acc.size());
+    }
+    if (r != CUDA_SUCCESS) {
+        if (ptr) { d.memUnmap(ptr, s.vmm_size); d.memAddressFree(ptr, s.vmm_size); }
+        d.memRelease(h);
+        return fail(r == CUDA_ERROR_OUT_OF_MEMORY ? FS3D_ERR_OOM : FS3D_ERR_CUDA, "mapping an exportable slab buffer failed: CUresult " + std::to_string((int)r));
+    }
+    s.vmm = true;
+    s.vmm_handle[b] = h;
+    s.buf[b] = reinterpret_cast<uint8_t *>(ptr);
+    return FS3D_OK;
+}
+static void vmm_free(Slab &s, int b) {
+    const DriverApi &d = driver_api();
+    if (!s.buf[b] || !d.ok) return;
+    d.memUnmap((CUdeviceptr)s.buf[b], s.vmm_size);
+    d.memAddressFree((CUdeviceptr)s.buf[b], s.vmm_size);
+    d.memRelease(s.vmm_handle[b]);
+    s.buf[b] = nullptr; s.vmm_handle[b] = 0;
+}
+
 static int init_slab(fs3d_world *w, Slab &s) {
     FS3D_CUDA(cudaSetDevice(s.device));
     const size_t pb = plane_bytes(w);
     s.bytes = pb * ((size_t)s.nzl + 2);
-    for (int b = 0; b < 2; ++b) FS3D_CUDA(cudaMalloc(&s.buf[b], s.bytes));
+    for (int b = 0; b < 2; ++b) {
+        if (w->desc.flags & FS3D_FLAG_EXPORTABLE) { int rc = vmm_alloc(w, s, b); if (rc) return rc; }
+        else FS3D_CUDA(cudaMalloc(&s.buf[b], s.bytes));
+    }
     FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_main, cudaStreamNonBlocking));
     FS3D_CUDA(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
     cudaEvent_t *evs[] = {&s.ev_edges, &s.ev_done, &s.ev_out_lo, &s.ev_out_hi};
@@ -209,7 +313,7 @@ static void free_slab(Slab &s) {
     cudaSetDevice(s.device);
     if (s.s_main) cudaStreamSynchronize(s.s_main);
     if (s.s_comm) cudaStreamSynchronize(s.s_comm);
-    for (int b = 0; b < 2; ++b) if (s.buf[b]) cudaFree(s.buf[b]);
+    for (int b = 0; b < 2; ++b) if (s.buf[b]) { if (s.vmm) vmm_free(s, b); else cudaFree(s.buf[b]); }
     for (Slab::Peer *pr : {&s.peer_lo, &s.peer_hi}) {
         if (!pr->valid || !pr->ipc) continue;
         for (int b = 0; b < 2; ++b) if (pr->buf[b]) cudaIpcCloseMemHandle(pr->buf[b]);
@@ -1073,6 +1177,36 @@ int fs3d_volume_view(fs3d_world *w, int32_t slab, fs3d_view *out) {
     return FS3D_OK;
 }
 
+int fs3d_volume_export_fd(fs3d_world *w, int32_t slab, fs3d_export *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (slab < 0 || slab >= (int32_t)w->slabs.size()) return fail(FS3D_ERR_OUT_OF_RANGE, "slab index out of range");
+    Slab &s = w->slabs[slab];
+    if (!s.vmm) return fail(FS3D_ERR_UNSUPPORTED, "create the world with FS3D_FLAG_EXPORTABLE to export its buffers");
+    int rc = sync_all(w);
+    if (rc) return rc;
+    FS3D_CUDA(cudaSetDevice(s.device));
+    const DriverApi &d = driver_api();
+    int fds[2] = {-1, -1};
+    for (int b = 0; b < 2; ++b) {
+        CUresult r = d.memExportToShareableHandle(&fds[b], s.vmm_handle[b], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+        if (r != CUDA_SUCCESS) {
+            if (fds[0] >= 0) close(fds[0]);
+            return fail(FS3D_ERR_CUDA, "cuMemExportToShareableHandle: CUresult " + std::to_string((int)r));
+        }
+    }
+    out->fd[0] = fds[0]; out->fd[1] = fds[1];
+    out->alloc_bytes = s.vmm_size;
+    out->first_cell_offset = plane_bytes(w);         // local plane 0 is the ghost plane below the slab
+    out->front = (uint32_t)w->cur;
+    out->device = s.device;
+    out->nx = w->desc.nx; out->ny = w->desc.ny;
+    out->z0 = s.z0; out->z1 = s.z0 + s.nzl;
+    out->pitch_y = w->desc.nx;
+    out->pitch_z = plane_bytes(w);
+    out->step = w->step;
+    return FS3D_OK;
+}
+
 int fs3d_set_palette(fs3d_world *w, const float *rgba256x4) {
     if (!w || !rgba256x4) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
     std::memcpy(w->palette, rgba256x4, sizeof(w->palette));
@@ -1276,6 +1410,8 @@ int fs3d_slab_ipc_export(fs3d_world *w, void *blob, uint64_t blob_bytes) {
     if (w->slabs.size() != 1 || !w->external) return fail(FS3D_ERR_UNSUPPORTED, "needs a world made by fs3d_create_slab");
     if (blob_bytes < sizeof(IpcBlob)) return fail(FS3D_ERR_INVALID_ARG, "blob too small (need FS3D_IPC_BLOB_BYTES)");
     Slab &s = w->slabs[0];
+    if (s.vmm) return fail(FS3D_ERR_UNSUPPORTED, "FS3D_FLAG_EXPORTABLE buffers are exported with fs3d_volume_export_fd; CUDA IPC handles "
+                                                 "(the fused halo push between processes) need ordinary allocations");
     FS3D_CUDA(cudaSetDevice(s.device));
     IpcBlob b{};
     b.magic = 0xF53D1BCu; b.nzl = s.nzl; b.z0 = s.z0; b.cur = (uint32_t)w->cur;

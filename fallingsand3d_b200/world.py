@@ -19,6 +19,7 @@ FLAG_SKIP_SETTLED = 1
 FLAG_NO_FUSE = 2
 FLAG_NO_PEER_PUSH = 4
 FLAG_PEER_PUSH_SHARED_DEVICE = 8
+FLAG_EXPORTABLE = 16
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
@@ -190,6 +191,14 @@ class VoxelWorld:
         v = _lib.View()
         _check(self._lib.fs3d_volume_view(self._h, slab, C.byref(v)))
         return {k: getattr(v, k) for k, _ in _lib.View._fields_}
+
+    def volume_export_fd(self, slab=0):
+        """The slab's two buffers as POSIX file descriptors (needs FLAG_EXPORTABLE); the caller closes them."""
+        e = _lib.Export()
+        _check(self._lib.fs3d_volume_export_fd(self._h, slab, C.byref(e)))
+        d = {k: getattr(e, k) for k, _ in _lib.Export._fields_ if k != "fd"}
+        d["fd"] = (int(e.fd[0]), int(e.fd[1]))
+        return d
 
     def set_palette(self, rgba):
         p = np.ascontiguousarray(rgba, dtype=np.float32)

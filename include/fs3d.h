@@ -64,6 +64,9 @@ extern "C" {
 #define FS3D_FLAG_PEER_PUSH_SHARED_DEVICE 8u /* n_gpus > 1 with several slabs on ONE device: use the fused halo push
                                         anyway (default there: peer copies).  Lets a one-GPU box run the PUSH kernels. */
 
+#define FS3D_FLAG_EXPORTABLE    16u  /* allocate the slab buffers through the driver's virtual-memory-management API so that
+                                        fs3d_volume_export_fd can hand them to another API or process as file descriptors */
+
 /* scene ids for fs3d_generate (SCHEDULE.md §5) */
 #define FS3D_SCENE_EMPTY        0
 #define FS3D_SCENE_SAND_BLOCK   1
@@ -91,6 +94,30 @@ typedef struct {
     uint64_t pitch_y, pitch_z;/* bytes between rows / planes */
     uint64_t step;            /* step index the view corresponds to */
 } fs3d_view;
+
+/* The two buffers of one slab as POSIX file descriptors (hand-off of the volume to a real Vulkan
+ * consumer).  The world is double-buffered: `front` says which of the two holds the current step; after every pass
+ * the other one does (fs3d_step(w, n) makes ceil(n / 2) passes when it starts on an even step).  Each descriptor
+ * refers to an allocation of alloc_bytes; cell (0, 0, z0) sits first_cell_offset bytes into it, then pitch_y / pitch_z
+ * as in fs3d_view.  Import with
+ *   - Vulkan:  VkImportMemoryFdInfoKHR{handleType = VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT, fd} chained into
+ *              VkMemoryAllocateInfo{allocationSize = alloc_bytes}, bound to a VkBuffer created with
+ *              VkExternalMemoryBufferCreateInfo (INTEGRATION.md has the engine-side patch), or
+ *   - CUDA in another process:  cuMemImportFromShareableHandle + cuMemAddressReserve / cuMemMap / cuMemSetAccess
+ *              (tests/vmm_import_child.py does exactly this and reproduces the digest).
+ * The caller owns the descriptors (close() them; an import takes its own reference).  Synchronise (fs3d_sync) before
+ * the consumer reads; the library does not know about foreign readers. */
+typedef struct {
+    int32_t  fd[2];
+    uint64_t alloc_bytes;
+    uint64_t first_cell_offset;
+    uint32_t front;           /* index into fd[] of the buffer holding step `step` */
+    int32_t  device;
+    uint32_t nx, ny;
+    uint32_t z0, z1;
+    uint64_t pitch_y, pitch_z;
+    uint64_t step;
+} fs3d_export;
 
 /* Camera of shaders/fs_raymarch.{vert,frag}: origin + aspect; yaw is the engine's camRot.y
  * (renderer.cpp:460-467), which fs_raymarch itself ignores (0 reproduces the shader). */
@@ -166,6 +193,7 @@ int  fs3d_activity(fs3d_world *w, uint64_t *tiles_run, uint64_t *tiles_total);
 /* ---- renderer hand-off ---- */
 int  fs3d_num_slabs(fs3d_world *w, int32_t *out);
 int  fs3d_volume_view(fs3d_world *w, int32_t slab, fs3d_view *out);
+int  fs3d_volume_export_fd(fs3d_world *w, int32_t slab, fs3d_export *out);   /* needs FS3D_FLAG_EXPORTABLE */
 int  fs3d_set_palette(fs3d_world *w, const float *rgba256x4);
 int  fs3d_raymarch(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height,
                    uint32_t mode, uint8_t *host_rgba8);

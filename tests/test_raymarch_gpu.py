@@ -135,3 +135,34 @@ def test_sdf_mode_equals_the_reference_shader_frames(fs3d):
             want[idx] = encode8_linear(red)
             assert np.array_equal(img[..., 0].reshape(-1), want)
             assert not img[..., 1].any() and not img[..., 2].any() and (img[..., 3] == 255).all()
+
+
+# ---- the same independent checks (closed-form axis rays, float64 sampled walk) against the CUDA kernel itself ----
+def _gpu_render(fs3d, g, seed=1):
+    w = fs3d.VoxelWorld(g.shape[2], g.shape[1], g.shape[0], seed=seed)
+    w.upload(g)
+
+    def render(pos, width, height, aspect, yaw_deg=0.0):
+        return w.raymarch(pos=pos, yaw_deg=yaw_deg, aspect=aspect, width=width, height=height, mode=fs3d.RM_VOXELS, with_depth=True)
+    return w, render
+
+
+def test_cuda_voxel_dda_closed_form_axis_rays(fs3d, oracle):
+    from tests.test_raymarch_oracle import _dda_scene, check_axis_rays
+    g = _dda_scene(oracle)
+    w, render = _gpu_render(fs3d, g)
+    try:
+        check_axis_rays(render, oracle, g)
+    finally:
+        w.close()
+
+
+def test_cuda_voxel_dda_agrees_with_float64_sampling(fs3d, oracle):
+    from tests.test_raymarch_oracle import _dda_scene, check_sampled_rays
+    g = _dda_scene(oracle)
+    w, render = _gpu_render(fs3d, g)
+    try:
+        for cam in (dict(pos=(0.0, 0.0, -1.6), aspect=16.0 / 9.0), dict(pos=(0.3, -0.25, -1.2), aspect=1.5, yaw_deg=17.0)):
+            check_sampled_rays(render, oracle, g, cam, 160, 90)
+    finally:
+        w.close()

@@ -132,3 +132,81 @@ def test_oracle_matches_live_reference_shader_when_built(oracle):
         img, depth = oracle.raymarch(None, mode=0, with_depth=True, **cam)
         assert np.array_equal(f[..., 0] > 0, np.isfinite(depth))
         assert np.array_equal(img[..., 0], np.where(f[..., 0] > 0, encode8_linear(f[..., 0]), 0))
+
+
+# ---- independent checks of the voxel DDA (oracle/oracle_np_dda.py): closed-form axis rays and float64 sampling ----
+def _dda_scene(oracle):
+    g = oracle.generate(64, 48, 40, 4, 3)          # MIXED_NOISE: floor, obstacles, boxes, noise above
+    g[:, :, 10:14] = 0                             # some empty columns (misses)
+    return g
+
+
+def check_axis_rays(render, oracle, g, n_cols=60):
+    """render(pos, width, height, aspect) -> (img, depth); closed-form answer for the 1 x 1 image on the optical axis"""
+    from oracle import oracle_np_dda as dda
+    nz, ny, nx = g.shape
+    pal = oracle.default_palette()
+    rng = np.random.default_rng(1)
+    seen_miss = seen_hit = 0
+    for _ in range(n_cols):
+        i, j = int(rng.integers(nx)), int(rng.integers(ny))
+        rgb, t = dda.analytic_axis_ray(g, i, j, pal)
+        img, depth = render(dda.column_camera(i, j, nx, ny, nz), 1, 1, 1.0)
+        if rgb is None:
+            assert np.isinf(depth[0, 0]) and tuple(img[0, 0, :3]) == (0, 0, 0), (i, j)
+            seen_miss += 1
+            continue
+        assert depth[0, 0] == np.float32(t), (i, j, depth[0, 0], t)        # h is a power of two: exact in float32
+        want = np.clip(np.floor(rgb * 255.0 + 0.5), 0, 255)
+        assert np.all(np.abs(img[0, 0, :3].astype(np.int64) - want) <= 1), (i, j, img[0, 0], want)
+        seen_hit += 1
+    assert seen_hit > 20 and seen_miss > 0
+
+
+def check_sampled_rays(render, oracle, g, cam, width, height, n_pix=150):
+    """the DDA's hit cell (recovered from its depth) equals the first cell a float64 sampled walk enters"""
+    from oracle import oracle_np_dda as dda
+    nz, ny, nx = g.shape
+    img, depth = render(cam["pos"], width, height, cam["aspect"], cam.get("yaw_deg", 0.0))
+    rng = np.random.default_rng(2)
+    h, e = dda.box(nx, ny, nz)
+    checked = 0
+    for _ in range(n_pix * 4):
+        px, py = int(rng.integers(width)), int(rng.integers(height))
+        d = dda.pixel_ray(px, py, width, height, cam["aspect"], cam.get("yaw_deg", 0.0))
+        ref = dda.sample_march(g, cam["pos"], d)
+        t = float(depth[py, px])
+        if ref is None:
+            assert np.isinf(t), (px, py)
+            continue
+        assert np.isfinite(t), (px, py, ref)
+        if dda.entry_point_margin(cam["pos"], d, t, nx, ny, nz) < 0.02:
+            continue                                  # grazing a cell edge: either neighbour is a legitimate answer
+        # the cell just behind the DDA's entry point
+        p = (np.asarray(cam["pos"]) + (t + 1e-4 * h) * d + e) / h
+        cell = (int(np.floor(p[0])), ny - 1 - int(np.floor(p[1])), int(np.floor(p[2])))
+        assert cell == ref[:3], (px, py, cell, ref)
+        assert abs(t - ref[3]) < h / 16, (px, py, t, ref[3])
+        assert tuple(img[py, px, :3]) != (0, 0, 0)
+        checked += 1
+        if checked >= n_pix:
+            break
+    assert checked >= 40
+
+
+def _oracle_render(oracle, g):
+    def render(pos, width, height, aspect, yaw_deg=0.0):
+        return oracle.raymarch(g, pos=pos, yaw_deg=yaw_deg, aspect=aspect, width=width, height=height, mode=1, with_depth=True)
+    return render
+
+
+def test_voxel_dda_closed_form_axis_rays(oracle):
+    g = _dda_scene(oracle)
+    check_axis_rays(_oracle_render(oracle, g), oracle, g)
+
+
+@pytest.mark.parametrize("cam", [dict(pos=(0.0, 0.0, -1.6), aspect=16.0 / 9.0), dict(pos=(0.3, -0.25, -1.2), aspect=1.5, yaw_deg=17.0),
+                                 dict(pos=(-0.9, 0.2, -0.9), aspect=1.0, yaw_deg=40.0)])
+def test_voxel_dda_agrees_with_float64_sampling(oracle, cam):
+    g = _dda_scene(oracle)
+    check_sampled_rays(_oracle_render(oracle, g), oracle, g, cam, 160, 90)
