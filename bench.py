@@ -321,6 +321,33 @@ def big_grid_block(args, world_size, rank, hbm_peak):
                     "is the same at every N"}
 
 
+def materials8_block(args, hbm_peak):
+    """Schedule version 2 (FS3D_FLAG_MATERIALS8: eight materials on three bit-planes, SCHEDULE.md §7) on the same grid size:
+    the MIXED8 scene, fused and unfused, beside version 1's numbers — same bytes per voxel, ~1.5x the integer work."""
+    import numpy as np
+    import fallingsand3d_b200 as fs3d
+    n, K = args.size, args.m8_steps
+    voxels = n * n * n
+    out = {"grid": [n, n, n], "scene": "MIXED8 (MIXED + gas / oil / honey / gravel boxes + RANDOM8 noise in the upper half)",
+           "schedule_version": 2, "steps": K, "warmup": 4}
+    try:
+        for name, flags in (("fused", 0), ("single_step", fs3d.FLAG_NO_FUSE)):
+            with fs3d.VoxelWorld(n, n, n, seed=1, flags=fs3d.FLAG_MATERIALS8 | flags) as w:
+                w.generate(fs3d.SCENE_MIXED8, 1)
+                h0 = w.histogram()
+                w.step(4)
+                w.sync()
+                ms, launches = w.step_timed(K)
+                assert np.array_equal(w.histogram(), h0), "material counts changed: invalid run"
+                a = 2.0 * voxels * K / (ms * 1e-3) / 1e9
+                out[name] = {"ms_per_step": ms / K, "value": voxels * K / (ms * 1e-3), "gpu_launches": int(launches),
+                             "achieved": a, "frac": a / hbm_peak, "digest": hex(w.digest())}
+        assert out["fused"]["digest"] == out["single_step"]["digest"], "fused and unfused version-2 runs disagree"
+    except Exception as e:
+        out["failed"] = repr(e)[:200]
+    return out
+
+
 def ours(args):
     import numpy as np
     import torch
@@ -494,6 +521,8 @@ def ours(args):
     extra = {}
     if args.big_steps > 0 and n != args.big_size:
         extra[f"size_{args.big_size}"] = big_grid_block(args, world_size, rank, hbm_peak)
+    if args.m8_steps > 0 and world_size == 1:
+        extra["materials8"] = materials8_block(args, hbm_peak)
 
     if rank != 0:
         if world_size > 1:
@@ -561,6 +590,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused-only", action="store_true", help="skip the unfused single-step measurement")
+    ap.add_argument("--m8-steps", type=int, default=20, help="timed steps of the schedule-version-2 block (N = 1); 0 = skip it")
     ap.add_argument("--big-size", type=int, default=4096, help="grid edge of the extra large-grid block (BASELINE configs[4])")
     ap.add_argument("--big-steps", type=int, default=20, help="timed steps of the extra large-grid block; 0 = skip it")
     args = ap.parse_args()

@@ -86,6 +86,7 @@ SIGNATURES = {
     "fs3d_load": (C.c_int, [_W, C.c_char_p]),
     "fs3d_last_error": (C.c_char_p, []),
     "fs3d_schedule_version": (C.c_int, []),
+    "fs3d_world_schedule_version": (C.c_int, [_W]),
 }
 
 _lib = None

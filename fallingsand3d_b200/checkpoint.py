@@ -56,6 +56,22 @@ def unpack2(packed, n):
     return out.reshape(-1)[:n]
 
 
+def pack4(cells):
+    """encoding 2 (schedule version 2, codes 0..7): two voxels per byte, voxel i in bits 4(i & 1) of byte i >> 1"""
+    c = np.ascontiguousarray(cells, dtype=np.uint8).reshape(-1, 2)
+    if (c > 7).any():
+        raise ValueError("material codes 8-255 are reserved")
+    return (c[:, 0] | (c[:, 1] << 4)).astype(np.uint8)
+
+
+def unpack4(packed, n):
+    p = np.frombuffer(packed, dtype=np.uint8) if not isinstance(packed, np.ndarray) else packed
+    out = np.empty((p.size, 2), dtype=np.uint8)
+    out[:, 0] = p & 15
+    out[:, 1] = p >> 4
+    return out.reshape(-1)[:n]
+
+
 def read_header(path):
     with open(path, "rb") as f:
         raw = f.read(HEADER.size)
@@ -70,30 +86,31 @@ def read_header(path):
 def read(path, verify=True):
     """-> (header dict, uint8 array of shape (z_end - z_begin, ny, nx))."""
     h = read_header(path)
-    if h["format_version"] != FORMAT_VERSION or h["encoding"] != 1:
+    if h["format_version"] != FORMAT_VERSION or h["encoding"] not in (1, 2) or h["encoding"] != h["schedule_version"]:
         raise ValueError(f"{path}: unknown checkpoint format version / encoding")
+    per_byte = 4 if h["encoding"] == 1 else 2
     nzh = h["z_end"] - h["z_begin"]
     n = h["nx"] * h["ny"] * nzh
     with open(path, "rb") as f:
         f.seek(HEADER.size)
         payload = f.read()
-    if len(payload) != h["payload_bytes"] or h["payload_bytes"] * 4 != n:
+    if len(payload) != h["payload_bytes"] or h["payload_bytes"] * per_byte != n:
         raise ValueError(f"{path}: payload size is inconsistent with the header")
-    grid = unpack2(payload, n).reshape(nzh, h["ny"], h["nx"])
+    grid = (unpack2 if h["encoding"] == 1 else unpack4)(payload, n).reshape(nzh, h["ny"], h["nx"])
     if verify and digest(grid, h["nx"], h["ny"], h["z_begin"]) != h["digest"]:
         raise ValueError(f"{path}: digest mismatch (corrupt checkpoint)")
     return h, grid
 
 
-def write(path, planes, nz=None, z_begin=0, step=0, seed=1):
-    """Writes planes (shape (nzh, ny, nx), uint8 codes 0..3) as a checkpoint fs3d_load accepts."""
+def write(path, planes, nz=None, z_begin=0, step=0, seed=1, schedule_version=SCHEDULE_VERSION):
+    """Writes planes (shape (nzh, ny, nx), uint8 codes 0..3; 0..7 with schedule_version=2) as a checkpoint fs3d_load accepts."""
     g = np.ascontiguousarray(planes, dtype=np.uint8)
     nzh, ny, nx = g.shape
     if nx % 32:
         raise ValueError("nx must be a multiple of 32")
-    payload = pack2(g)
-    hdr = HEADER.pack(MAGIC, FORMAT_VERSION, SCHEDULE_VERSION, nx, ny, nzh if nz is None else nz, z_begin,
-                      z_begin + nzh, 1, step, seed, digest(g, nx, ny, z_begin), payload.size, 0)
+    payload = pack2(g) if schedule_version == 1 else pack4(g)
+    hdr = HEADER.pack(MAGIC, FORMAT_VERSION, schedule_version, nx, ny, nzh if nz is None else nz, z_begin,
+                      z_begin + nzh, 1 if schedule_version == 1 else 2, step, seed, digest(g, nx, ny, z_begin), payload.size, 0)
     with open(path, "wb") as f:
         f.write(hdr)
         f.write(payload.tobytes())

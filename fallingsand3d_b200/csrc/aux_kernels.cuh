@@ -22,6 +22,15 @@ __device__ inline uint8_t random_cell(uint32_t key, int64_t x, int64_t y, int64_
     uint32_t u = hash3(key, (uint32_t)x, (uint32_t)y, (uint32_t)z) & 3u;
     return u == 0 ? FS3D_SAND : (u == 1 ? FS3D_WATER : FS3D_EMPTY);
 }
+__device__ __constant__ int c_gas_box[6]    = { 10, 26, 12, 19, 10, 26 };
+__device__ __constant__ int c_oil_box[6]    = { 34, 54, 36, 43, 10, 30 };
+__device__ __constant__ int c_honey_box[6]  = { 38, 50, 24, 31, 38, 54 };
+__device__ __constant__ int c_gravel_box[6] = { 12, 24, 36, 43, 38, 54 };
+__device__ __constant__ uint8_t c_pick8[16] = { FS3D_SAND, FS3D_SAND, FS3D_WATER, FS3D_WATER, FS3D_OIL, FS3D_GAS, FS3D_HONEY, FS3D_GRAVEL,
+                                                0, 0, 0, 0, 0, 0, 0, 0 };
+__device__ inline uint8_t random8_cell(uint32_t key, int64_t x, int64_t y, int64_t z) {
+    return c_pick8[(hash3(key, (uint32_t)x, (uint32_t)y, (uint32_t)z) >> 4) & 15u];
+}
 __device__ inline uint8_t mixed_cell(int64_t nx, int64_t ny, int64_t nz, int64_t x, int64_t y, int64_t z) {
     int64_t floor_h = ny / 64 > 1 ? ny / 64 : 1;
     if (y < floor_h) return FS3D_STONE;
@@ -41,6 +50,17 @@ __device__ inline uint8_t scene_cell(int scene, uint32_t key, int64_t nx, int64_
     case FS3D_SCENE_MIXED_NOISE: {
         uint8_t m = mixed_cell(nx, ny, nz, x, y, z);
         if (m == FS3D_EMPTY && y >= ny / 2) m = random_cell(key, x, y, z);
+        return m;
+    }
+    case FS3D_SCENE_RANDOM8: return random8_cell(key, x, y, z);
+    case FS3D_SCENE_MIXED8: {
+        uint8_t m = mixed_cell(nx, ny, nz, x, y, z);
+        if (m != FS3D_EMPTY) return m;
+        if (in_box(x, y, z, nx, ny, nz, c_gas_box)) return FS3D_GAS;
+        if (in_box(x, y, z, nx, ny, nz, c_oil_box)) return FS3D_OIL;
+        if (in_box(x, y, z, nx, ny, nz, c_honey_box)) return FS3D_HONEY;
+        if (in_box(x, y, z, nx, ny, nz, c_gravel_box)) return FS3D_GRAVEL;
+        if (y >= ny / 2) m = random8_cell(key, x, y, z);
         return m;
     }
     default: return FS3D_EMPTY;
@@ -75,12 +95,12 @@ __global__ void fill_kernel(uint8_t *p, uint64_t nbytes16, uint32_t pattern) {
         reinterpret_cast<uint4 *>(p)[v] = make_uint4(pattern, pattern, pattern, pattern);
 }
 
-// flag[0] |= 1 if any byte > 3
-__global__ void validate_kernel(const uint8_t *p, uint64_t n16, uint32_t *flag) {
+// flag[0] |= 1 if any byte has a bit of `bad_bits` set (0xFC..: codes > 3, schedule version 1; 0xF8..: codes > 7, version 2)
+__global__ void validate_kernel(const uint8_t *p, uint64_t n16, uint32_t bad_bits, uint32_t *flag) {
     uint32_t bad = 0;
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n16; v += (uint64_t)gridDim.x * blockDim.x) {
         uint4 q = reinterpret_cast<const uint4 *>(p)[v];
-        bad |= (q.x | q.y | q.z | q.w) & 0xFCFCFCFCu;
+        bad |= (q.x | q.y | q.z | q.w) & bad_bits;
     }
     if (__any_sync(0xFFFFFFFFu, bad != 0) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
 }
@@ -90,7 +110,7 @@ __global__ void histogram_kernel(const uint8_t *p, uint64_t n16, unsigned long l
     __shared__ unsigned int sh[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    unsigned int c[4] = {0, 0, 0, 0};
+    unsigned int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint32_t iter = 0;
     for (; v < n16; v += (uint64_t)gridDim.x * blockDim.x) {
@@ -98,9 +118,13 @@ __global__ void histogram_kernel(const uint8_t *p, uint64_t n16, unsigned long l
         uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if ((w[k] & 0xFCFCFCFCu) == 0) {
+            if ((w[k] & 0xF8F8F8F8u) == 0) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) c[(w[k] >> (8 * b)) & 3u]++;
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t m = (w[k] >> (8 * b)) & 7u;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) c[q] += m == (uint32_t)q ? 1u : 0u;      // registers, not local memory
+                }
             } else {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) atomicAdd(&sh[(w[k] >> (8 * b)) & 0xFFu], 1u);
@@ -108,12 +132,12 @@ __global__ void histogram_kernel(const uint8_t *p, uint64_t n16, unsigned long l
         }
         if (++iter == (1u << 20)) {  // keep 32-bit counters from overflowing on huge grids
 #pragma unroll
-            for (int m = 0; m < 4; ++m) { atomicAdd(&counts[m], (unsigned long long)c[m]); c[m] = 0; }
+            for (int m = 0; m < 8; ++m) { atomicAdd(&counts[m], (unsigned long long)c[m]); c[m] = 0; }
             iter = 0;
         }
     }
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
+    for (int m = 0; m < 8; ++m) {
         unsigned int s = c[m];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
         if ((threadIdx.x & 31) == 0 && s) atomicAdd(&counts[m], (unsigned long long)s);
@@ -166,6 +190,31 @@ __global__ void unpack2_kernel(const uint32_t *packed, uint64_t n16, uint8_t *ce
             const uint32_t b = (in >> (8 * k)) & 0xFFu;
             w[k] = (b & 3u) | (((b >> 2) & 3u) << 8) | (((b >> 4) & 3u) << 16) | (((b >> 6) & 3u) << 24);
         }
+        reinterpret_cast<uint4 *>(cells)[v] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// schedule version 2 checkpoints (encoding 2): 2 voxels per byte, voxel i of the stream in bits 4(i & 1) of byte i >> 1.
+// One thread packs 16 voxels (one uint4) into one uint2 / unpacks one uint2 into a uint4.
+__global__ void pack4_kernel(const uint8_t *cells, uint64_t n16, uint2 *packed) {
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n16; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 q = reinterpret_cast<const uint4 *>(cells)[v];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)     // bytes b0 b1 b2 b3 -> 16 bits: b0 | b1 << 4 | b2 << 8 | b3 << 12
+            h[k] = (w[k] & 15u) | (((w[k] >> 8) & 15u) << 4) | (((w[k] >> 16) & 15u) << 8) | (((w[k] >> 24) & 15u) << 12);
+        packed[v] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+    }
+}
+__global__ void unpack4_kernel(const uint2 *packed, uint64_t n16, uint8_t *cells) {
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n16; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint2 in = packed[v];
+        const uint32_t h[4] = {in.x & 0xFFFFu, in.x >> 16, in.y & 0xFFFFu, in.y >> 16};
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            w[k] = (h[k] & 15u) | (((h[k] >> 4) & 15u) << 8) | (((h[k] >> 8) & 15u) << 16) | (((h[k] >> 12) & 15u) << 24);
         reinterpret_cast<uint4 *>(cells)[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }

@@ -19,7 +19,7 @@
 
 #include "common.cuh"
 #include "aux_kernels.cuh"
-#include "step_kernel.cuh"
+#include "step_dispatch.cuh"
 #include "raymarch.cuh"
 
 namespace fs3d {
@@ -28,18 +28,6 @@ static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-#ifndef FS3D_STEP_THREADS
-#define FS3D_STEP_THREADS 256
-#endif
-constexpr int STEP_THREADS = FS3D_STEP_THREADS;         // J = 2 kernels (nx > 1024)
-#ifndef FS3D_STEP_THREADS_J1
-#define FS3D_STEP_THREADS_J1 384   // 12 warps per SM: 4.5 % faster than 256 x 2 CTAs at 1024^3 (profiles/r01d_experiments_xy_pair.txt)
-#endif
-constexpr int STEP_THREADS_J1 = FS3D_STEP_THREADS_J1;   // J = 1 kernels (nx <= 1024) on grids large enough to be bandwidth-bound
-// kernel shapes: jidx 0: J = 1 (nx <= 1024), 1: J = 2 (nx <= 2048), 2: J = 2 x 2 warps (nx <= 4096),
-//                3: J = 1 in STEP_THREADS-sized CTAs — small grids are launch/latency-bound and ran 15 % slower in 384-thread CTAs
-static int step_threads(int jidx) { return jidx == 0 ? STEP_THREADS_J1 : STEP_THREADS; }
-static uint32_t warps_per_pair(int jidx) { return jidx == 2 ? 2u : 1u; }
 constexpr uint64_t SMALL_GRID_VOXELS = 1ull << 27;      // per slab; 512^3 measured the same either way
 
 struct Slab {
@@ -109,6 +97,8 @@ struct fs3d_world {
     unsigned long long wait_target = 0;   // iterations each neighbour has delivered before the next pass
     bool ghosts_stale = false;   // slab world after fs3d_slab_step_host: fs3d_slab_push_halos must run before fs3d_step
     unsigned long long push_timeout_ns = 20000ull * 1000000ull;   // watchdog of the fused halo push (FS3D_PUSH_TIMEOUT_MS)
+    int version = 1;             // schedule version: 1 (four materials) or 2 (FS3D_FLAG_MATERIALS8: eight, SCHEDULE.md §7)
+    uint8_t max_material = FS3D_STONE;
     bool force_live = false;     // fs3d_step_host in flight: settled-tile plans treat every tile as live
     bool failed = false;         // the watchdog fired: cells are undefined, stepping is refused
 };
@@ -116,28 +106,9 @@ struct fs3d_world {
 namespace fs3d {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
-typedef void (*StepFn)(const StepParams);
-#define FS3D_TH(J) ((J) == 1 ? STEP_THREADS_J1 : STEP_THREADS)
-#define FS3D_ROW(J, XW, SK, PU) \
-    {{step_kernel<J, XW, 0, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, XW, 0, 1, SK, 1, PU, FS3D_TH(J)>}, \
-     {step_kernel<J, XW, 1, 0, SK, 1, PU, FS3D_TH(J)>, step_kernel<J, XW, 1, 1, SK, 1, PU, FS3D_TH(J)>}}
-#define FS3D_ROW2(J, XW, SK, PU) {step_kernel<J, XW, 0, 0, SK, 2, PU, FS3D_TH(J)>, step_kernel<J, XW, 1, 0, SK, 2, PU, FS3D_TH(J)>}
-#define FS3D_ROW_S(J, XW, SK, PU) \
-    {{step_kernel<J, XW, 0, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, XW, 0, 1, SK, 1, PU, STEP_THREADS>}, \
-     {step_kernel<J, XW, 1, 0, SK, 1, PU, STEP_THREADS>, step_kernel<J, XW, 1, 1, SK, 1, PU, STEP_THREADS>}}
-#define FS3D_ROW2_S(J, XW, SK, PU) {step_kernel<J, XW, 0, 0, SK, 2, PU, STEP_THREADS>, step_kernel<J, XW, 1, 0, SK, 2, PU, STEP_THREADS>}
-#define FS3D_SHAPES(M, SK, PU) {M(1, 1, SK, PU), M(2, 1, SK, PU), M(2, 2, SK, PU), M##_S(1, 1, SK, PU)}
-// ns = 1: one step (any parity); ns = 2: steps t, t + 1 fused, t even; push = fused halo push over peer memory
-static StepFn step_fn(int jidx, int ox, int todd, int skip, int ns, int push) {
-    static StepFn tab1[2][2][4][2][2] = {
-        {FS3D_SHAPES(FS3D_ROW, 0, 0), FS3D_SHAPES(FS3D_ROW, 1, 0)},
-        {FS3D_SHAPES(FS3D_ROW, 0, 1), FS3D_SHAPES(FS3D_ROW, 1, 1)},
-    };
-    static StepFn tab2[2][2][4][2] = {
-        {FS3D_SHAPES(FS3D_ROW2, 0, 0), FS3D_SHAPES(FS3D_ROW2, 1, 0)},
-        {FS3D_SHAPES(FS3D_ROW2, 0, 1), FS3D_SHAPES(FS3D_ROW2, 1, 1)},
-    };
-    return ns == 2 ? tab2[push][skip][jidx][ox] : tab1[push][skip][jidx][ox][todd];
+StepFn step_fn_v1(int jidx, int ox, int todd, int skip, int ns, int push) { return step_fn_of<Rules1>(jidx, ox, todd, skip, ns, push); }
+static StepFn step_fn(int version, int jidx, int ox, int todd, int skip, int ns, int push) {
+    return version == 2 ? step_fn_v2(jidx, ox, todd, skip, ns, push) : step_fn_v1(jidx, ox, todd, skip, ns, push);
 }
 #ifndef FS3D_HOST_CHUNK_MIB
 #define FS3D_HOST_CHUNK_MIB 256ull   // fs3d_step_host streams the grid in chunks of about this size (64 MiB measured 3 % slower)
@@ -277,8 +248,8 @@ static int init_slab(fs3d_world *w, Slab &s) {
                     for (int td = 0; td < (ns == 2 ? 1 : 2); ++td) {
                         int nb = 0;
                         const size_t smem = step_smem(w->jidx, pu);
-                        if (smem) FS3D_CUDA(cudaFuncSetAttribute(step_fn(w->jidx, ox, td, sk, ns, pu), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->jidx, ox, td, sk, ns, pu), step_threads(w->jidx), smem));
+                        if (smem) FS3D_CUDA(cudaFuncSetAttribute(step_fn(w->version, w->jidx, ox, td, sk, ns, pu), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        FS3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, step_fn(w->version, w->jidx, ox, td, sk, ns, pu), step_threads(w->jidx), smem));
                         s.blocks_per_sm[pu][ns - 1][sk][ox][td] = std::max(nb, 1);
                     }
     FS3D_CUDA(cudaMalloc(&s.d_flags, 8 * sizeof(unsigned long long)));
@@ -344,8 +315,10 @@ static void default_palette(float *p) {
     // EMPTY transparent black, SAND, WATER, STONE; the rest a grey ramp.  A host that owns the
     // reference's colors[256] (renderer.cpp:136-393) passes it to fs3d_set_palette instead.
     for (int i = 0; i < 256; ++i) { float g = i / 255.0f; p[4 * i] = g; p[4 * i + 1] = g; p[4 * i + 2] = g; p[4 * i + 3] = 1.0f; }
-    const float base[4][4] = {{0, 0, 0, 0}, {0.86f, 0.72f, 0.40f, 1}, {0.15f, 0.40f, 0.85f, 1}, {0.45f, 0.45f, 0.48f, 1}};
-    for (int i = 0; i < 4; ++i) for (int c = 0; c < 4; ++c) p[4 * i + c] = base[i][c];
+    const float base[8][4] = {{0, 0, 0, 0}, {0.86f, 0.72f, 0.40f, 1}, {0.15f, 0.40f, 0.85f, 1}, {0.45f, 0.45f, 0.48f, 1},
+                              {0.80f, 0.90f, 0.75f, 1} /* GAS */, {0.25f, 0.20f, 0.10f, 1} /* OIL */,
+                              {0.95f, 0.65f, 0.10f, 1} /* HONEY */, {0.55f, 0.50f, 0.45f, 1} /* GRAVEL */};
+    for (int i = 0; i < 8; ++i) for (int c = 0; c < 4; ++c) p[4 * i + c] = base[i][c];
 }
 
 static int finish_create(fs3d_world *w) {
@@ -353,6 +326,7 @@ static int finish_create(fs3d_world *w) {
         const long long v = std::atoll(ms);
         if (v > 0) w->push_timeout_ns = (unsigned long long)v * 1000000ull;
     }
+    if (w->desc.flags & FS3D_FLAG_MATERIALS8) { w->version = 2; w->max_material = FS3D_GRAVEL; }
     const uint32_t wpr = w->desc.nx / 32;
     w->jidx = wpr <= 32 ? 0 : (wpr <= 64 ? 1 : 2);
     w->lpr = wpr < 32 ? wpr : 32;
@@ -443,7 +417,7 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
         w->launches++;
         p.runs = q.runs; p.nruns = q.nruns;
     }
-    step_fn(w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, step_smem(w->jidx, push), s.s_main>>>(p);
+    step_fn(w->version, w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, step_smem(w->jidx, push), s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
     w->launches++;
     return FS3D_OK;
@@ -786,6 +760,7 @@ extern "C" {
 
 const char *fs3d_last_error(void) { return g_err.c_str(); }
 int fs3d_schedule_version(void) { return FS3D_SCHEDULE_VERSION; }
+int fs3d_world_schedule_version(fs3d_world *w) { return w ? w->version : 0; }
 
 int fs3d_create(const fs3d_desc *desc, fs3d_world **out) {
     if (!out) return fail(FS3D_ERR_INVALID_ARG, "out is NULL");
@@ -959,6 +934,11 @@ int fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kernel
 }
 
 // ---- cell access -----------------------------------------------------------------------------------
+static const char *bad_material_msg(const fs3d_world *w) {
+    return w->version == 2 ? "material codes 8-255 are reserved" : "material codes 4-255 are reserved (codes 4-7 need FS3D_FLAG_MATERIALS8)";
+}
+static uint32_t bad_bits(const fs3d_world *w) { return w->version == 2 ? 0xF8F8F8F8u : 0xFCFCFCFCu; }   // bits no valid code has
+
 static int check_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z) {
     if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
     if (x >= w->desc.nx || y >= w->desc.ny || z >= w->desc.nz) return fail(FS3D_ERR_OUT_OF_RANGE, "cell outside the grid");
@@ -968,7 +948,7 @@ static int check_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z) {
 int fs3d_set_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t m) {
     int rc = check_cell(w, x, y, z);
     if (rc) return rc;
-    if (m > FS3D_STONE) return fail(FS3D_ERR_BAD_MATERIAL, "material codes 4-255 are reserved");
+    if (m > w->max_material) return fail(FS3D_ERR_BAD_MATERIAL, bad_material_msg(w));
     Slab *s = slab_of_z(w, z);
     if (!s) return FS3D_OK;   // not in this rank's slab: nothing to do
     rc = sync_all(w);
@@ -996,7 +976,7 @@ int fs3d_get_cell(fs3d_world *w, uint32_t x, uint32_t y, uint32_t z, uint8_t *m)
 
 int fs3d_fill_box(fs3d_world *w, const uint32_t lo[3], const uint32_t hi[3], uint8_t m) {
     if (!w || !lo || !hi) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
-    if (m > FS3D_STONE) return fail(FS3D_ERR_BAD_MATERIAL, "material codes 4-255 are reserved");
+    if (m > w->max_material) return fail(FS3D_ERR_BAD_MATERIAL, bad_material_msg(w));
     if (hi[0] > w->desc.nx || hi[1] > w->desc.ny || hi[2] > w->desc.nz || lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2])
         return fail(FS3D_ERR_OUT_OF_RANGE, "box outside the grid");
     if (lo[0] == hi[0] || lo[1] == hi[1] || lo[2] == hi[2]) return FS3D_OK;
@@ -1016,7 +996,7 @@ int fs3d_fill_box(fs3d_world *w, const uint32_t lo[3], const uint32_t hi[3], uin
 
 int fs3d_paint_sphere(fs3d_world *w, int32_t cx, int32_t cy, int32_t cz, uint32_t radius, uint8_t m, int only_empty) {
     if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
-    if (m > FS3D_STONE) return fail(FS3D_ERR_BAD_MATERIAL, "material codes 4-255 are reserved");
+    if (m > w->max_material) return fail(FS3D_ERR_BAD_MATERIAL, bad_material_msg(w));
     if (radius > (1u << 20)) return fail(FS3D_ERR_INVALID_ARG, "brush radius too large");
     int rc = sync_all(w);
     if (rc) return rc;
@@ -1035,7 +1015,9 @@ int fs3d_paint_sphere(fs3d_world *w, int32_t cx, int32_t cy, int32_t cz, uint32_
 
 int fs3d_generate(fs3d_world *w, int scene_id, uint64_t seed) {
     if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
-    if (scene_id < 0 || scene_id > FS3D_SCENE_MIXED_NOISE) return fail(FS3D_ERR_INVALID_ARG, "unknown scene id");
+    if (scene_id < 0 || scene_id > FS3D_SCENE_MIXED8) return fail(FS3D_ERR_INVALID_ARG, "unknown scene id");
+    if (scene_id > FS3D_SCENE_MIXED_NOISE && w->version != 2)
+        return fail(FS3D_ERR_BAD_MATERIAL, "scenes RANDOM8 / MIXED8 hold materials 4-7: create the world with FS3D_FLAG_MATERIALS8");
     int rc = sync_all(w);
     if (rc) return rc;
     const uint32_t key = step_key(seed, 0, 7);
@@ -1066,7 +1048,7 @@ int fs3d_upload(fs3d_world *w, const uint8_t *host) {
         uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
         FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
         uint64_t n16 = pb * s.nzl / 16;
-        validate_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, back), n16, flag);
+        validate_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, back), n16, bad_bits(w), flag);
         FS3D_CUDA(cudaGetLastError());
     }
     bool bad = false;
@@ -1077,7 +1059,7 @@ int fs3d_upload(fs3d_world *w, const uint8_t *host) {
         FS3D_CUDA(cudaStreamSynchronize(s.s_main));
         bad = bad || f != 0;
     }
-    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, "upload contains material codes 4-255 (reserved)");
+    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, std::string("upload: ") + bad_material_msg(w));
     w->cur = back;
     return refresh_ghosts(w);
 }
@@ -1333,7 +1315,7 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
         FS3D_CUDA(cudaMemcpyAsync(src + off, host_in + pb * (size_t)(lo - 1), bytes, cudaMemcpyHostToDevice, s.s_h2d));
         FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
         FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
-        validate_kernel<<<grid_for(bytes / 16, s), 256, 0, s.s_main>>>(src + off, bytes / 16, flag);
+        validate_kernel<<<grid_for(bytes / 16, s), 256, 0, s.s_main>>>(src + off, bytes / 16, bad_bits(w), flag);
         FS3D_CUDA(cudaGetLastError());
         rc = launch_pairs(w, s, p0, p1, ns);
         if (rc) { w->force_live = false; return rc; }
@@ -1351,7 +1333,7 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
     w->step += (uint64_t)ns;
     rc = touch_all_tiles(w);
     if (rc) return rc;
-    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, "host grid contains material codes 4-255 (reserved); the world now holds "
+    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, std::string("host grid: ") + bad_material_msg(w) + "; the world now holds "
                                                 "undefined cells - upload or generate before stepping again");
     return FS3D_OK;
 }
@@ -1625,7 +1607,7 @@ struct CkptHeader {
     uint32_t schedule_version;    // FS3D_SCHEDULE_VERSION the state was produced under
     uint32_t nx, ny, nz;          // global grid
     uint32_t z_begin, z_end;      // planes in this file
-    uint32_t encoding;            // 1 = 2-bit packed, x fastest
+    uint32_t encoding;            // 1 = 2 bits per voxel (schedule version 1), 2 = 4 bits per voxel (version 2), x fastest
     uint64_t step, seed;
     uint64_t digest;              // fs3d_digest of these planes (global indices): checked on load
     uint64_t payload_bytes;
@@ -1654,31 +1636,34 @@ int fs3d_save(fs3d_world *w, const char *path) {
     const uint32_t zb = w->slabs.front().z0, ze = w->slabs.back().z0 + w->slabs.back().nzl;
     CkptHeader h{};
     std::memcpy(h.magic, "FS3DCKPT", 8);
-    h.format_version = FS3D_CKPT_VERSION; h.schedule_version = FS3D_SCHEDULE_VERSION;
+    // schedule version 1: 2 bits per voxel (encoding 1, div = 4); version 2: 4 bits per voxel (encoding 2, div = 2)
+    const uint32_t div = w->version == 2 ? 2u : 4u;
+    h.format_version = FS3D_CKPT_VERSION; h.schedule_version = (uint32_t)w->version;
     h.nx = w->desc.nx; h.ny = w->desc.ny; h.nz = w->desc.nz; h.z_begin = zb; h.z_end = ze;
-    h.encoding = 1; h.step = w->step; h.seed = w->desc.seed; h.digest = dg;
-    h.payload_bytes = pb / 4 * (uint64_t)(ze - zb);      // nx % 32 == 0, so a plane packs to whole bytes
+    h.encoding = w->version == 2 ? 2u : 1u; h.step = w->step; h.seed = w->desc.seed; h.digest = dg;
+    h.payload_bytes = pb / div * (uint64_t)(ze - zb);    // nx % 32 == 0, so a plane packs to whole bytes
     File out;
     out.f = std::fopen(path, "wb");
     if (!out.f) return fail(FS3D_ERR_IO, std::string("cannot open ") + path + " for writing");
     bool io_ok = std::fwrite(&h, sizeof(h), 1, out.f) == 1;
     // pack on the device, stream to the file in chunks of whole planes (<= ~64 MiB packed)
-    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / 4));
-    std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / 4));
+    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / div));
+    std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / div));
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
         DevBuf packed;
         const uint32_t cp = std::min(planes_per_chunk, s.nzl);
-        FS3D_CUDA(cudaMalloc(&packed.p, (size_t)cp * (pb / 4)));
+        FS3D_CUDA(cudaMalloc(&packed.p, (size_t)cp * (pb / div)));
         for (uint32_t z = 0; z < s.nzl && io_ok; z += cp) {
             const uint32_t n = std::min(cp, s.nzl - z);
-            const uint64_t n16 = pb * n / 16;
-            pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur) + pb * z, n16, packed.p);
+            const uint64_t n16 = pb * n / 16, nbytes = n16 * (16 / div);
+            if (w->version == 2) pack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur) + pb * z, n16, reinterpret_cast<uint2 *>(packed.p));
+            else pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur) + pb * z, n16, packed.p);
             FS3D_CUDA(cudaGetLastError());
             w->launches++;
-            FS3D_CUDA(cudaMemcpyAsync(host.data(), packed.p, n16 * 4, cudaMemcpyDeviceToHost, s.s_main));
+            FS3D_CUDA(cudaMemcpyAsync(host.data(), packed.p, nbytes, cudaMemcpyDeviceToHost, s.s_main));
             FS3D_CUDA(cudaStreamSynchronize(s.s_main));
-            io_ok = std::fwrite(host.data(), 1, n16 * 4, out.f) == n16 * 4;
+            io_ok = std::fwrite(host.data(), 1, nbytes, out.f) == nbytes;
         }
     }
     io_ok = (out.close() == 0) && io_ok;
@@ -1696,32 +1681,34 @@ int fs3d_load(fs3d_world *w, const char *path) {
         return fail(FS3D_ERR_IO, std::string(path) + " is not an fs3d checkpoint");
     const size_t pb = plane_bytes(w);
     const uint32_t zb = w->slabs.front().z0, ze = w->slabs.back().z0 + w->slabs.back().nzl;
-    if (h.format_version != FS3D_CKPT_VERSION || h.encoding != 1)
+    const uint32_t div = w->version == 2 ? 2u : 4u;
+    if (h.format_version != FS3D_CKPT_VERSION || (h.encoding != 1 && h.encoding != 2))
         return fail(FS3D_ERR_INVALID_ARG, "unknown checkpoint format version / encoding");
-    if (h.schedule_version != FS3D_SCHEDULE_VERSION)
+    if (h.schedule_version != (uint32_t)w->version || h.encoding != (w->version == 2 ? 2u : 1u))
         return fail(FS3D_ERR_INVALID_ARG, "checkpoint was written under another schedule version");
     if (h.nx != w->desc.nx || h.ny != w->desc.ny || h.nz != w->desc.nz)
         return fail(FS3D_ERR_INVALID_ARG, "checkpoint grid differs from the world's");
     if (h.z_begin != zb || h.z_end != ze) return fail(FS3D_ERR_INVALID_ARG, "checkpoint holds other z-planes than this world");
-    if (h.payload_bytes != pb / 4 * (uint64_t)(ze - zb)) return fail(FS3D_ERR_INVALID_ARG, "checkpoint payload size is inconsistent");
+    if (h.payload_bytes != pb / div * (uint64_t)(ze - zb)) return fail(FS3D_ERR_INVALID_ARG, "checkpoint payload size is inconsistent");
     int rc = sync_all(w);
     if (rc) return rc;
     // unpack into the BACK buffer, verify the digest there, then flip: a bad file leaves the world untouched
     const int back = w->cur ^ 1;
-    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / 4));
-    std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / 4));
+    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / div));
+    std::vector<uint8_t> host((size_t)std::min<uint64_t>(planes_per_chunk, ze - zb) * (pb / div));
     uint64_t sum = 0;
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
         DevBuf packed;
         const uint32_t cp = std::min(planes_per_chunk, s.nzl);
-        FS3D_CUDA(cudaMalloc(&packed.p, (size_t)cp * (pb / 4)));
+        FS3D_CUDA(cudaMalloc(&packed.p, (size_t)cp * (pb / div)));
         for (uint32_t z = 0; z < s.nzl; z += cp) {
             const uint32_t n = std::min(cp, s.nzl - z);
-            const uint64_t n16 = pb * n / 16;
-            if (std::fread(host.data(), 1, n16 * 4, in.f) != n16 * 4) return fail(FS3D_ERR_IO, std::string(path) + " is truncated");
-            FS3D_CUDA(cudaMemcpyAsync(packed.p, host.data(), n16 * 4, cudaMemcpyHostToDevice, s.s_main));
-            unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(packed.p, n16, owned_ptr(w, s, back) + pb * z);
+            const uint64_t n16 = pb * n / 16, nbytes = n16 * (16 / div);
+            if (std::fread(host.data(), 1, nbytes, in.f) != nbytes) return fail(FS3D_ERR_IO, std::string(path) + " is truncated");
+            FS3D_CUDA(cudaMemcpyAsync(packed.p, host.data(), nbytes, cudaMemcpyHostToDevice, s.s_main));
+            if (w->version == 2) unpack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint2 *>(packed.p), n16, owned_ptr(w, s, back) + pb * z);
+            else unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(packed.p, n16, owned_ptr(w, s, back) + pb * z);
             FS3D_CUDA(cudaGetLastError());
             w->launches++;
             FS3D_CUDA(cudaStreamSynchronize(s.s_main));      // `host` is reused by the next chunk

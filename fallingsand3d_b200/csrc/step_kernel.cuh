@@ -25,8 +25,46 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "bitslice.cuh"
+#include "bitslice3.cuh"
 
 namespace fs3d {
+
+// ---- rule sets: what a kernel instantiation needs to know about the cells it marches -------------------------------
+// Rules1 = schedule version 1 (four materials, two bit-planes, SCHEDULE.md §1-5); Rules3 = schedule version 2 (eight
+// materials, three rank-encoded bit-planes, SCHEDULE.md §7).  Everything else in the step kernel — the march, the
+// loads and stores, the halo push, the settled-tile bookkeeping, the word-boundary exchanges — is shared.
+struct Rules1 {
+    using Cell = P2;
+    static constexpr bool COLUMN_FORM = true;          // the per-column XY form (xy_substep) exists for two planes only
+    static constexpr uint32_t NB_STONE = 0xFFu;         // packed voxel-0 bits of a word beyond the wall
+    static __device__ __forceinline__ Cell stone() { return {ONES, ONES}; }
+    static __device__ __forceinline__ Cell pack(const uint32_t (&w)[8]) { return fs3d::pack(w); }
+    static __device__ __forceinline__ void unpack(Cell c, uint32_t (&w)[8]) { fs3d::unpack(c, w); }
+    static __device__ __forceinline__ uint32_t zy(Cell &a, Cell &b, Cell &c, Cell &d, uint32_t rw) { return block_rule(a, b, c, d, rw); }
+    static __device__ __forceinline__ uint32_t xy0(Cell &U0, Cell &L0, Cell &U1, Cell &L1, uint32_t r0, uint32_t r1) { return xy_pair_substep0(U0, L0, U1, L1, r0, r1); }
+    static __device__ __forceinline__ uint32_t first_bits(Cell U0, Cell L0, Cell U1, Cell L1) { return xy_first_bits(U0, L0, U1, L1); }
+    static __device__ __forceinline__ uint32_t xy1(Cell &U0, Cell &L0, Cell &U1, Cell &L1, uint32_t r0, uint32_t r1, uint32_t nb, uint32_t &carry) {
+        return xy_pair_substep1(U0, L0, U1, L1, r0, r1, nb, carry);
+    }
+    static __device__ __forceinline__ void post1(Cell &U0, Cell &L0, Cell &U1, Cell &L1, uint32_t pb) { xy_pair_post1(U0, L0, U1, L1, pb); }
+    static __device__ __forceinline__ uint32_t wall_first(uint32_t first, uint32_t &en) { return xy_wall_first(first, en); }
+};
+struct Rules3 {
+    using Cell = P3;
+    static constexpr bool COLUMN_FORM = false;
+    static constexpr uint32_t NB_STONE = NB_STONE3;
+    static __device__ __forceinline__ Cell stone() { return {ONES, ONES, ONES}; }
+    static __device__ __forceinline__ Cell pack(const uint32_t (&w)[8]) { return pack3(w); }
+    static __device__ __forceinline__ void unpack(Cell c, uint32_t (&w)[8]) { unpack3(c, w); }
+    static __device__ __forceinline__ uint32_t zy(Cell &a, Cell &b, Cell &c, Cell &d, uint32_t rw) { return block_rule3(a, b, c, d, rw, coin2_word(rw)); }
+    static __device__ __forceinline__ uint32_t xy0(Cell &U0, Cell &L0, Cell &U1, Cell &L1, uint32_t r0, uint32_t r1) { return xy3_pair_substep0(U0, L0, U1, L1, r0, r1); }
+    static __device__ __forceinline__ uint32_t first_bits(Cell U0, Cell L0, Cell U1, Cell L1) { return xy3_first_bits(U0, L0, U1, L1); }
+    static __device__ __forceinline__ uint32_t xy1(Cell &U0, Cell &L0, Cell &U1, Cell &L1, uint32_t r0, uint32_t r1, uint32_t nb, uint32_t &carry) {
+        return xy3_pair_substep1(U0, L0, U1, L1, r0, r1, nb, carry);
+    }
+    static __device__ __forceinline__ void post1(Cell &U0, Cell &L0, Cell &U1, Cell &L1, uint32_t pb) { xy3_pair_post1(U0, L0, U1, L1, pb); }
+    static __device__ __forceinline__ uint32_t wall_first(uint32_t first, uint32_t &en) { return xy3_wall_first(first, en); }
+};
 
 struct StepParams {
     const uint8_t *src;      // slab buffer incl. ghost planes; local plane 0 = ghost-low
@@ -191,8 +229,9 @@ struct Raw { uint32_t w[J][2][2][8]; };   // [word][row l/r][plane lo/hi][8 x u3
 // single warp moves by shuffle at the word boundary in XY sub-steps with odd x-offset.  It goes through
 // 32-bit shared-memory mailboxes, tagged with a sequence number and polled by the consumer — no
 // barrier, so the two warps only ever wait for the one value they need.
-template <int J, int XW, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
+template <class R, int J, int XW, int OX, int TODD, int SKIP, int NS, int PUSH, int THREADS>
 __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepParams p) {
+    using Cell = typename R::Cell;
     static_assert(NS == 1 || (NS == 2 && TODD == 0), "a fused pair of steps starts on an even step");
     static_assert(XW == 1 || (XW == 2 && J > 1 && THREADS % 64 == 0), "warp pairs live in one CTA");
     constexpr bool XCH = XW == 2 && OX == 1;    // edge words cross the warp-pair boundary
@@ -376,12 +415,12 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
             ++kc;
         };
 
-        P2 prev1[J][2], c2[J][2], c3[J][2], lo[J][2], hi[J][2];
+        Cell prev1[J][2], c2[J][2], c3[J][2], lo[J][2], hi[J][2];
         auto reset_carry = [&]() {
 #pragma unroll
             for (int j = 0; j < J; ++j)
 #pragma unroll
-                for (int r = 0; r < 2; ++r) { prev1[j][r] = {ONES, ONES}; c2[j][r] = {ONES, ONES}; c3[j][r] = {ONES, ONES}; }
+                for (int r = 0; r < 2; ++r) { prev1[j][r] = R::stone(); c2[j][r] = R::stone(); c3[j][r] = R::stone(); }
         };
 
         // Odd x-offset has two implementations of the XY sub-step (even offset always uses xy_pair_substep0):
@@ -393,9 +432,9 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
         // column form where two warps per scheduler must hide the extra round trip (fused XW = 1 kernels, 5 %).
         // -DFS3D_XY_PAIR_OX1=0/1 forces one of them everywhere.
 #ifdef FS3D_XY_PAIR_OX1
-        constexpr bool PAIR1 = FS3D_XY_PAIR_OX1 != 0;
+        constexpr bool PAIR1 = !R::COLUMN_FORM || FS3D_XY_PAIR_OX1 != 0;
 #else
-        constexpr bool PAIR1 = NS == 1 || XW == 2 || SKIP == 1;
+        constexpr bool PAIR1 = !R::COLUMN_FORM || NS == 1 || XW == 2 || SKIP == 1;
 #endif
         // One-way message between the two warps of a pair (XW = 2): a tagged 32-bit mailbox in shared memory.
         // Both warps count messages alike; messages alternate direction (pre: half 1 -> 0, post: half 0 -> 1),
@@ -414,17 +453,17 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
         };
         // XY sub-step on (upper, lower) of both rows at once, every block evaluated once (bitslice.cuh,
         // xy_pair_substep*); the upper row is plane yu
-        auto do_xy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu, uint32_t key) {
+        auto do_xy = [&](Cell (&up)[J][2], Cell (&lw)[J][2], uint32_t yu, uint32_t key) {
             uint32_t en = 0;
             uint32_t rw[J][2];
 #pragma unroll
             for (int j = 0; j < J; ++j)
 #pragma unroll
                 for (int r = 0; r < 2; ++r) rw[j][r] = hash_word(key + hxy[j][r] + yu * HC2);
-            if (OX == 0) {
+            if constexpr (OX == 0) {
 #pragma unroll
-                for (int j = 0; j < J; ++j) en |= xy_pair_substep0(up[j][0], lw[j][0], up[j][1], lw[j][1], rw[j][0], rw[j][1]);
-            } else if (!PAIR1) {
+                for (int j = 0; j < J; ++j) en |= R::xy0(up[j][0], lw[j][0], up[j][1], lw[j][1], rw[j][0], rw[j][1]);
+            } else if constexpr (!PAIR1) {
                 // per-column evaluation (xy_substep): one exchange of edge words, every block computed from both columns
                 uint32_t e[J][2];
                 uint32_t xe[2] = {EDGE_STONE, EDGE_STONE};
@@ -463,15 +502,15 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                 // evaluation (shuffle up) or, at the grid wall, the fall-only rule
                 uint32_t first[J], carry[J];
 #pragma unroll
-                for (int j = 0; j < J; ++j) first[j] = xy_first_bits(up[j][0], lw[j][0], up[j][1], lw[j][1]);
-                uint32_t xin = 0xFFu;
+                for (int j = 0; j < J; ++j) first[j] = R::first_bits(up[j][0], lw[j][0], up[j][1], lw[j][1]);
+                uint32_t xin = R::NB_STONE;
                 if (XCH) xin = xmail(1u, 0u, first[0]);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     uint32_t b = __shfl_down_sync(ONES, first[j], 1);
                     if (J > 1 && j < J - 1) { uint32_t t = __shfl_sync(ONES, first[j + 1], 0); if (lane == 31) b = t; }
                     if (XCH && j == J - 1 && half == 0u && lane == 31u) b = xin;
-                    en |= xy_pair_substep1(up[j][0], lw[j][0], up[j][1], lw[j][1], rw[j][0], rw[j][1], hasn[j] ? b : 0xFFu, carry[j]);
+                    en |= R::xy1(up[j][0], lw[j][0], up[j][1], lw[j][1], rw[j][0], rw[j][1], hasn[j] ? b : R::NB_STONE, carry[j]);
                 }
                 if (XCH) xin = xmail(0u, 31u, carry[J - 1]);
 #pragma unroll
@@ -481,21 +520,21 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                     if (XCH && j == 0 && half == 1u && lane == 0u) a = xin;
                     if (j == 0) {           // only a row's first word can sit at the wall
                         uint32_t enw = 0;
-                        const uint32_t wall = xy_wall_first(first[0], enw);
+                        const uint32_t wall = R::wall_first(first[0], enw);
                         if (!hasp[0]) { a = wall; en |= enw; }
                     }
-                    xy_pair_post1(up[j][0], lw[j][0], up[j][1], lw[j][1], a);
+                    R::post1(up[j][0], lw[j][0], up[j][1], lw[j][1], a);
                 }
             }
             return en;
         };
         // ZY sub-step across the two rows, upper row is plane yu
-        auto do_zy = [&](P2 (&up)[J][2], P2 (&lw)[J][2], uint32_t yu, uint32_t key) {
+        auto do_zy = [&](Cell (&up)[J][2], Cell (&lw)[J][2], uint32_t yu, uint32_t key) {
             uint32_t en = 0;
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 uint32_t rw = hash_word(key + hzy[j] + yu * HC2);
-                en |= block_rule(up[j][0], up[j][1], lw[j][0], lw[j][1], rw);
+                en |= R::zy(up[j][0], up[j][1], lw[j][0], lw[j][1], rw);
             }
             return en;
         };
@@ -539,10 +578,10 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
             for (int j = 0; j < J; ++j)
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    lo[j][r] = pack(raw.w[j][r][0]);
-                    hi[j][r] = pack(raw.w[j][r][1]);
-                    if (!(wok[j] && y1 < p.ny))      lo[j][r] = {ONES, ONES};   // STONE outside the grid
-                    if (!(wok[j] && y1 + 1u < p.ny)) hi[j][r] = {ONES, ONES};
+                    lo[j][r] = R::pack(raw.w[j][r][0]);
+                    hi[j][r] = R::pack(raw.w[j][r][1]);
+                    if (!(wok[j] && y1 < p.ny))      lo[j][r] = R::stone();   // STONE outside the grid
+                    if (!(wok[j] && y1 + 1u < p.ny)) hi[j][r] = R::stone();
                 }
 
             // the next iteration's loads are in flight while this one is evaluated
@@ -580,13 +619,13 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
                             uint32_t o[8];
                             const uint32_t ya = y1 - LAG - 1u, yb = y1 - LAG;    // wrap to huge when negative
                             if (ya < p.ny) {
-                                unpack(NS == 2 ? c3[j][r] : prev1[j][r], o);
+                                R::unpack(NS == 2 ? c3[j][r] : prev1[j][r], o);
                                 st256(drow[j][r] + (size_t)ya * row_bytes, o);
                                 if (PUSH && r == rlo) st256(drow[j][r] + (size_t)ya * row_bytes + dlo, o);
                                 if (PUSH && r == rhi) st256(drow[j][r] + (size_t)ya * row_bytes + dhi, o);
                             }
                             if (yb < p.ny) {
-                                unpack(NS == 2 ? c2[j][r] : lo[j][r], o);
+                                R::unpack(NS == 2 ? c2[j][r] : lo[j][r], o);
                                 st256(drow[j][r] + (size_t)yb * row_bytes, o);
                                 if (PUSH && r == rlo) st256(drow[j][r] + (size_t)yb * row_bytes + dlo, o);
                                 if (PUSH && r == rhi) st256(drow[j][r] + (size_t)yb * row_bytes + dhi, o);
@@ -652,7 +691,7 @@ struct PlanParams {
     uint32_t *runs, *nruns, *nruns_next;
 };
 
-__global__ void skip_plan_kernel(const PlanParams q) {
+static __global__ void skip_plan_kernel(const PlanParams q) {   // static: step_kernel.cuh is included by two translation units
     const uint32_t npairs = q.pair_end - q.pair_begin;
     const uint32_t npg = (npairs + q.groups - 1) / q.groups;
     const uint32_t blk = 1u << q.blk_log2;

@@ -14,12 +14,15 @@ import numpy as np
 from . import _lib
 
 EMPTY, SAND, WATER, STONE = 0, 1, 2, 3
+GAS, OIL, HONEY, GRAVEL = 4, 5, 6, 7            # schedule version 2 (FLAG_MATERIALS8), SCHEDULE.md §7
 SCENE_EMPTY, SCENE_SAND_BLOCK, SCENE_MIXED, SCENE_RANDOM, SCENE_MIXED_NOISE = 0, 1, 2, 3, 4
+SCENE_RANDOM8, SCENE_MIXED8 = 5, 6
 FLAG_SKIP_SETTLED = 1
 FLAG_NO_FUSE = 2
 FLAG_NO_PEER_PUSH = 4
 FLAG_PEER_PUSH_SHARED_DEVICE = 8
 FLAG_EXPORTABLE = 16
+FLAG_MATERIALS8 = 32
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
@@ -131,6 +134,10 @@ class VoxelWorld:
 
     def sync(self):
         _check(self._lib.fs3d_sync(self._h))
+
+    @property
+    def schedule_version(self):
+        return int(self._lib.fs3d_world_schedule_version(self._h))
 
     @property
     def step_index(self):

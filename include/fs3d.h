@@ -37,13 +37,18 @@
 extern "C" {
 #endif
 
-#define FS3D_SCHEDULE_VERSION 1
+#define FS3D_SCHEDULE_VERSION 1      /* the default rule set; worlds made with FS3D_FLAG_MATERIALS8 run version 2 */
 
 /* materials (SCHEDULE.md §1) */
 #define FS3D_EMPTY 0
 #define FS3D_SAND  1
 #define FS3D_WATER 2
 #define FS3D_STONE 3
+/* schedule version 2 only (SCHEDULE.md §7; FS3D_FLAG_MATERIALS8) */
+#define FS3D_GAS    4   /* lighter than EMPTY: rises, spreads sideways */
+#define FS3D_OIL    5   /* liquid, floats on WATER */
+#define FS3D_HONEY  6   /* viscous liquid between WATER and SAND: spreads sideways a quarter as often */
+#define FS3D_GRAVEL 7   /* granular, denser than SAND, never slides diagonally */
 
 /* error codes */
 #define FS3D_OK                 0
@@ -67,12 +72,18 @@ extern "C" {
 #define FS3D_FLAG_EXPORTABLE    16u  /* allocate the slab buffers through the driver's virtual-memory-management API so that
                                         fs3d_volume_export_fd can hand them to another API or process as file descriptors */
 
+#define FS3D_FLAG_MATERIALS8    32u  /* schedule version 2: eight materials (codes 0-7) on three bit-planes — a separate set
+                                        of kernels, so worlds that hold only codes 0-3 pay nothing for it.  A version-2
+                                        world that holds only codes 0-3 evolves exactly like a version-1 world. */
+
 /* scene ids for fs3d_generate (SCHEDULE.md §5) */
 #define FS3D_SCENE_EMPTY        0
 #define FS3D_SCENE_SAND_BLOCK   1
 #define FS3D_SCENE_MIXED        2
 #define FS3D_SCENE_RANDOM       3
 #define FS3D_SCENE_MIXED_NOISE  4
+#define FS3D_SCENE_RANDOM8      5   /* FS3D_FLAG_MATERIALS8 worlds only (SCHEDULE.md §7) */
+#define FS3D_SCENE_MIXED8       6
 
 typedef struct fs3d_world fs3d_world;
 
@@ -260,9 +271,10 @@ int  fs3d_frame_resolve(fs3d_world *w, uint8_t *host_rgba8);
  *   offset  0  char[8]  "FS3DCKPT"
  *           8  u32 format version (FS3D_CKPT_VERSION)   12  u32 schedule version
  *          16  u32 nx, ny, nz                            28  u32 z_begin, z_end (planes in the file)
- *          36  u32 encoding (1)                          40  u64 step index   48  u64 seed
+ *          36  u32 encoding (1 | 2)                          40  u64 step index   48  u64 seed
  *          56  u64 digest of these planes                64  u64 payload bytes   72  u64 reserved (0)
- *   offset 80  payload: cells in x-fastest order, 2 bits each, cell i in bits 2(i & 3) of byte i >> 2
+ *   offset 80  payload: cells in x-fastest order; encoding 1 (schedule version 1): 2 bits each, cell i in bits 2(i & 3) of
+ *              byte i >> 2; encoding 2 (schedule version 2, FS3D_FLAG_MATERIALS8): 4 bits each, cell i in bits 4(i & 1) of byte i >> 1
  * fs3d_load restores cells, step index and seed (so the run continues bit-identically), verifies
  * dimensions, plane range, schedule version and the digest, and leaves the world untouched on any
  * error.  Ranks of a fused-halo-push world call fs3d_slab_push_halos + barrier afterwards. */
@@ -273,6 +285,7 @@ int  fs3d_load(fs3d_world *w, const char *path);
 
 const char *fs3d_last_error(void);
 int  fs3d_schedule_version(void);
+int  fs3d_world_schedule_version(fs3d_world *w);   /* 1, or 2 for FS3D_FLAG_MATERIALS8 worlds */
 
 #ifdef __cplusplus
 }

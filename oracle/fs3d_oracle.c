@@ -19,7 +19,7 @@
 #include <stddef.h>
 #include <string.h>
 
-enum { EMPTY = 0, SAND = 1, WATER = 2, STONE = 3 };
+enum { EMPTY = 0, SAND = 1, WATER = 2, STONE = 3, GAS = 4, OIL = 5, HONEY = 6, GRAVEL = 7 };
 enum { AXIS_XY = 0, AXIS_ZY = 1 };
 
 /* ---- SCHEDULE.md §3: the coin ------------------------------------------------------------ */
@@ -55,6 +55,19 @@ int fs3d_oracle_coin(uint64_t seed, uint64_t t, uint32_t axis, uint32_t X, uint3
     return coin_at(fs3d_oracle_key(seed, t, axis), X, Y, Z);
 }
 
+/* SCHEDULE.md §7 (version 2): the second coin of a block, drawn from the same hash word through C2 */
+static int coin2_at(uint32_t key, int64_t X, int64_t Y, int64_t Z) {
+    uint32_t x = (uint32_t)X;
+    uint32_t bit = 8u * (x & 3u) + ((x >> 2) & 7u);
+    uint32_t v = fs3d_oracle_hash(key, x >> 5, (uint32_t)Y, (uint32_t)Z) * 0x9E3779B1u;
+    v ^= v >> 15;
+    return (int)((v >> bit) & 1u);
+}
+
+int fs3d_oracle_coin2(uint64_t seed, uint64_t t, uint32_t axis, uint32_t X, uint32_t Y, uint32_t Z) {
+    return coin2_at(fs3d_oracle_key(seed, t, axis), X, Y, Z);
+}
+
 /* ---- SCHEDULE.md §1-2: the block rule ------------------------------------------------------ */
 
 static int density(uint8_t m) { return m == SAND ? 2 : (m == WATER ? 1 : 0); }
@@ -67,11 +80,38 @@ static int heavier(uint8_t u, uint8_t l) {
 
 static void swap8(uint8_t *p, uint8_t *q) { uint8_t t = *p; *p = *q; *q = t; }
 
+/* ---- SCHEDULE.md §7: schedule version 2, eight materials ----------------------------------------
+ * rank (density order): GAS 0 < EMPTY 1 < OIL 2 < WATER 3 < HONEY 4 < SAND 5 < GRAVEL 6; STONE never moves.
+ * A cell yields to a denser mover only if it is not granular / solid: GAS, EMPTY, OIL, WATER, HONEY. */
+static const int RANK_V2[8] = { /*EMPTY*/ 1, /*SAND*/ 5, /*WATER*/ 3, /*STONE*/ 7, /*GAS*/ 0, /*OIL*/ 2, /*HONEY*/ 4, /*GRAVEL*/ 6 };
+static int yields_v2(uint8_t m) { return m == GAS || m == EMPTY || m == OIL || m == WATER || m == HONEY; }
+static int heavier_v2(uint8_t u, uint8_t l) {
+    if (u == STONE || !yields_v2(l)) return 0;
+    return RANK_V2[u & 7] > RANK_V2[l & 7];
+}
+static int block_rule_v2(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, uint32_t key, int64_t X, int64_t Y, int64_t Z) {
+    int enabled = 0;
+    /* F */
+    if (heavier_v2(*a, *c)) { swap8(a, c); enabled = 1; }
+    if (heavier_v2(*b, *d)) { swap8(b, d); enabled = 1; }
+    /* D: GRAVEL never slides */
+    if (heavier_v2(*a, *d) && *b != STONE && *a != GRAVEL) { swap8(a, d); enabled = 1; }
+    else if (heavier_v2(*b, *c) && *a != STONE && *b != GRAVEL) { swap8(b, c); enabled = 1; }
+    /* L: any two different yielding cells mix sideways under the coin; HONEY is viscous: it also needs the second coin */
+    if (*a != *b && yields_v2(*a) && yields_v2(*b)) {
+        enabled = 1;
+        int go = coin_at(key, X, Y, Z);
+        if (go && (*a == HONEY || *b == HONEY)) go = coin2_at(key, X, Y, Z);
+        if (go) swap8(a, b);
+    }
+    return enabled;
+}
+
 /* Applies F, D, L to one block whose upper-left cell `a` is global cell (X, Y, Z).  Returns 1 if the
  * block is "enabled" (something would move with coin = 1), else 0.  The coin is only drawn when L is
  * enabled: then a and b are WATER/EMPTY, i.e. both inside the grid, so (X, Y, Z) is in range
  * (SCHEDULE.md §3 "the coin only matters when both upper cells are inside the grid"). */
-static int block_rule(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, uint32_t key, int64_t X, int64_t Y, int64_t Z) {
+static int block_rule_v1(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, uint32_t key, int64_t X, int64_t Y, int64_t Z) {
     int enabled = 0;
     /* F */
     if (heavier(*a, *c)) { swap8(a, c); enabled = 1; }
@@ -87,12 +127,16 @@ static int block_rule(uint8_t *a, uint8_t *b, uint8_t *c, uint8_t *d, uint32_t k
     return enabled;
 }
 
+#define block_rule(a, b, c, d, key, X, Y, Z) \
+    (g->version == 2 ? block_rule_v2(a, b, c, d, key, X, Y, Z) : block_rule_v1(a, b, c, d, key, X, Y, Z))
+
 /* ---- grid access: arr holds global planes [zbase, zbase + narr) --------------------------- */
 
 typedef struct {
     uint8_t *arr;
     int64_t nx, ny, nzg;   /* global dims */
     int64_t zbase, narr;   /* planes held */
+    int version;           /* schedule version: 1 (four materials) or 2 (eight, SCHEDULE.md §7) */
 } grid_t;
 
 static uint8_t rd(const grid_t *g, int64_t x, int64_t y, int64_t z) {
@@ -182,10 +226,10 @@ static int64_t substep_zy(const grid_t *g, uint32_t key, int oz, int oy, int64_t
  * A whole grid is zbase = 0, narr = nzg, own = [0, nzg).  Returns the number of enabled blocks
  * that intersect the owned planes' dependency region (0 ⇒ nothing could move this step).
  */
-int64_t fs3d_oracle_step_range(uint8_t *arr, int64_t nx, int64_t ny, int64_t nzg,
-                               int64_t zbase, int64_t narr, int64_t own_lo, int64_t own_hi,
-                               uint64_t seed, uint64_t t) {
-    grid_t g = { arr, nx, ny, nzg, zbase, narr };
+int64_t fs3d_oracle_step_range_v(uint8_t *arr, int64_t nx, int64_t ny, int64_t nzg,
+                                 int64_t zbase, int64_t narr, int64_t own_lo, int64_t own_hi,
+                                 uint64_t seed, uint64_t t, int version) {
+    grid_t g = { arr, nx, ny, nzg, zbase, narr, version };
     int hoff = (int)((t >> 1) & 1);
     uint32_t kxy = fs3d_oracle_key(seed, t, AXIS_XY), kzy = fs3d_oracle_key(seed, t, AXIS_ZY);
     int64_t en = 0;
@@ -199,13 +243,28 @@ int64_t fs3d_oracle_step_range(uint8_t *arr, int64_t nx, int64_t ny, int64_t nzg
     return en;
 }
 
+int64_t fs3d_oracle_step_range(uint8_t *arr, int64_t nx, int64_t ny, int64_t nzg,
+                               int64_t zbase, int64_t narr, int64_t own_lo, int64_t own_hi,
+                               uint64_t seed, uint64_t t) {
+    return fs3d_oracle_step_range_v(arr, nx, ny, nzg, zbase, narr, own_lo, own_hi, seed, t, 1);
+}
+
+int64_t fs3d_oracle_step_v(uint8_t *grid, int64_t nx, int64_t ny, int64_t nz, uint64_t seed, uint64_t t, int version) {
+    return fs3d_oracle_step_range_v(grid, nx, ny, nz, 0, nz, 0, nz, seed, t, version);
+}
+
 int64_t fs3d_oracle_step(uint8_t *grid, int64_t nx, int64_t ny, int64_t nz, uint64_t seed, uint64_t t) {
-    return fs3d_oracle_step_range(grid, nx, ny, nz, 0, nz, 0, nz, seed, t);
+    return fs3d_oracle_step_v(grid, nx, ny, nz, seed, t, 1);
+}
+
+void fs3d_oracle_run_v(uint8_t *grid, int64_t nx, int64_t ny, int64_t nz, uint64_t seed,
+                       uint64_t t0, uint64_t nsteps, int version) {
+    for (uint64_t i = 0; i < nsteps; ++i) fs3d_oracle_step_v(grid, nx, ny, nz, seed, t0 + i, version);
 }
 
 void fs3d_oracle_run(uint8_t *grid, int64_t nx, int64_t ny, int64_t nz, uint64_t seed,
                      uint64_t t0, uint64_t nsteps) {
-    for (uint64_t i = 0; i < nsteps; ++i) fs3d_oracle_step(grid, nx, ny, nz, seed, t0 + i);
+    fs3d_oracle_run_v(grid, nx, ny, nz, seed, t0, nsteps, 1);
 }
 
 /* ---- SCHEDULE.md §5: scenes ---------------------------------------------------------------- */
@@ -229,6 +288,16 @@ static uint8_t random_cell(uint64_t seed, int64_t x, int64_t y, int64_t z) {
     return u == 0 ? SAND : (u == 1 ? WATER : EMPTY);
 }
 
+/* SCHEDULE.md §7 scenes: RANDOM8 draws from all seven movable materials, half of the cells stay EMPTY */
+static uint8_t random8_cell(uint64_t seed, int64_t x, int64_t y, int64_t z) {
+    static const uint8_t PICK[16] = { SAND, SAND, WATER, WATER, OIL, GAS, HONEY, GRAVEL, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY, EMPTY };
+    return PICK[(fs3d_oracle_hash(fs3d_oracle_key(seed, 0, 7), (uint32_t)x, (uint32_t)y, (uint32_t)z) >> 4) & 15u];
+}
+static const int GAS_BOX[6]    = { 10, 26, 12, 19, 10, 26 };   /* under the first stone ledge: rises and pools below it */
+static const int OIL_BOX[6]    = { 34, 54, 36, 43, 10, 30 };
+static const int HONEY_BOX[6]  = { 38, 50, 24, 31, 38, 54 };
+static const int GRAVEL_BOX[6] = { 12, 24, 36, 43, 38, 54 };
+
 static uint8_t mixed_cell(int64_t nx, int64_t ny, int64_t nz, int64_t x, int64_t y, int64_t z) {
     int64_t floor_h = ny / 64 > 1 ? ny / 64 : 1;
     if (y < floor_h) return STONE;
@@ -249,6 +318,17 @@ uint8_t fs3d_oracle_scene_cell(int scene, uint64_t seed, int64_t nx, int64_t ny,
     case 4: {
         uint8_t m = mixed_cell(nx, ny, nz, x, y, z);
         if (m == EMPTY && y >= ny / 2) m = random_cell(seed, x, y, z);
+        return m;
+    }
+    case 5: return random8_cell(seed, x, y, z);
+    case 6: {   /* MIXED8: the MIXED layout, boxes of the four new materials, RANDOM8 noise in the empty upper half */
+        uint8_t m = mixed_cell(nx, ny, nz, x, y, z);
+        if (m != EMPTY) return m;
+        if (in_box(x, y, z, nx, ny, nz, GAS_BOX)) return GAS;
+        if (in_box(x, y, z, nx, ny, nz, OIL_BOX)) return OIL;
+        if (in_box(x, y, z, nx, ny, nz, HONEY_BOX)) return HONEY;
+        if (in_box(x, y, z, nx, ny, nz, GRAVEL_BOX)) return GRAVEL;
+        if (y >= ny / 2) m = random8_cell(seed, x, y, z);
         return m;
     }
     default: return EMPTY;

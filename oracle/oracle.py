@@ -75,6 +75,14 @@ def lib():
         L.fs3d_oracle_step_range.argtypes = [u8p, i64, i64, i64, i64, i64, i64, i64, u64, u64]
         L.fs3d_oracle_run.restype = None
         L.fs3d_oracle_run.argtypes = [u8p, i64, i64, i64, u64, u64, u64]
+        L.fs3d_oracle_step_v.restype = i64
+        L.fs3d_oracle_step_v.argtypes = [u8p, i64, i64, i64, u64, u64, C.c_int]
+        L.fs3d_oracle_run_v.restype = None
+        L.fs3d_oracle_run_v.argtypes = [u8p, i64, i64, i64, u64, u64, u64, C.c_int]
+        L.fs3d_oracle_step_range_v.restype = i64
+        L.fs3d_oracle_step_range_v.argtypes = [u8p, i64, i64, i64, i64, i64, i64, i64, u64, u64, C.c_int]
+        L.fs3d_oracle_coin2.restype = C.c_int
+        L.fs3d_oracle_coin2.argtypes = [u64, u64, u32, u32, u32, u32]
         L.fs3d_oracle_scene_cell.restype = C.c_uint8
         L.fs3d_oracle_scene_cell.argtypes = [C.c_int, u64, i64, i64, i64, i64, i64, i64]
         L.fs3d_oracle_generate.restype = None
@@ -106,22 +114,22 @@ def _chk(grid):
     return grid.shape  # (nz, ny, nx)
 
 
-def step(grid, seed, t):
-    """One in-place step of a whole (nz, ny, nx) uint8 grid. Returns the enabled-block count."""
+def step(grid, seed, t, version=1):
+    """One in-place step of a whole (nz, ny, nx) uint8 grid under schedule `version`. Returns the enabled-block count."""
     nz, ny, nx = _chk(grid)
-    return lib().fs3d_oracle_step(_ptr(grid), nx, ny, nz, seed, t)
+    return lib().fs3d_oracle_step_v(_ptr(grid), nx, ny, nz, seed, t, version)
 
 
-def run(grid, seed, t0, nsteps):
+def run(grid, seed, t0, nsteps, version=1):
     nz, ny, nx = _chk(grid)
-    lib().fs3d_oracle_run(_ptr(grid), nx, ny, nz, seed, t0, nsteps)
+    lib().fs3d_oracle_run_v(_ptr(grid), nx, ny, nz, seed, t0, nsteps, version)
     return grid
 
 
-def step_range(arr, nzg, zbase, own_lo, own_hi, seed, t):
+def step_range(arr, nzg, zbase, own_lo, own_hi, seed, t, version=1):
     """One step of a slab array holding global planes [zbase, zbase + arr.shape[0])."""
     narr, ny, nx = _chk(arr)
-    return lib().fs3d_oracle_step_range(_ptr(arr), nx, ny, nzg, zbase, narr, own_lo, own_hi, seed, t)
+    return lib().fs3d_oracle_step_range_v(_ptr(arr), nx, ny, nzg, zbase, narr, own_lo, own_hi, seed, t, version)
 
 
 def generate(nx, ny, nz, scene, seed, zlo=0, zhi=None):
@@ -165,6 +173,10 @@ def coin(seed, t, axis, x, y, z):
     return lib().fs3d_oracle_coin(seed, t, axis, x, y, z)
 
 
+def coin2(seed, t, axis, x, y, z):
+    return lib().fs3d_oracle_coin2(seed, t, axis, x, y, z)
+
+
 def default_palette():
     p = np.zeros((256, 4), dtype=np.float32)
     g = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
@@ -173,6 +185,10 @@ def default_palette():
     p[1] = (0.86, 0.72, 0.40, 1)
     p[2] = (0.15, 0.40, 0.85, 1)
     p[3] = (0.45, 0.45, 0.48, 1)
+    p[4] = (0.80, 0.90, 0.75, 1)      # GAS
+    p[5] = (0.25, 0.20, 0.10, 1)      # OIL
+    p[6] = (0.95, 0.65, 0.10, 1)      # HONEY
+    p[7] = (0.55, 0.50, 0.45, 1)      # GRAVEL
     return p
 
 

@@ -6,7 +6,7 @@ kernels are three differently-shaped implementations of one spec and must agree 
 """
 import numpy as np
 
-EMPTY, SAND, WATER, STONE = 0, 1, 2, 3
+EMPTY, SAND, WATER, STONE, GAS, OIL, HONEY, GRAVEL = 0, 1, 2, 3, 4, 5, 6, 7
 M64 = (1 << 64) - 1
 
 
@@ -44,6 +44,41 @@ def coins(k, X, Y, Z):
     return ((h >> bit) & np.uint32(1)).astype(bool)
 
 
+def coins2(k, X, Y, Z):
+    """SCHEDULE.md §7: the second coin, the same hash word passed through C2(v) = (v * 0x9E3779B1) ^ ((v * 0x9E3779B1) >> 15)."""
+    X = X.astype(np.int64)
+    xu = (X & 0xFFFFFFFF).astype(np.uint32)
+    bit = (np.uint32(8) * (xu & np.uint32(3)) + ((xu >> np.uint32(2)) & np.uint32(7))).astype(np.uint32)
+    h = hash_words(k, xu >> np.uint32(5), (Y.astype(np.int64) & 0xFFFFFFFF).astype(np.uint32),
+                   (Z.astype(np.int64) & 0xFFFFFFFF).astype(np.uint32))
+    with np.errstate(over="ignore"):
+        v = (h * np.uint32(0x9E3779B1)).astype(np.uint32)
+    v ^= v >> np.uint32(15)
+    return ((v >> bit) & np.uint32(1)).astype(bool)
+
+
+# ---- schedule version 2 (SCHEDULE.md §7): eight materials, as lookup tables over the codes ----
+_RANK2 = np.array([1, 5, 3, 7, 0, 2, 4, 6], dtype=np.int64)                     # by material code
+_YIELDS2 = np.array([1, 0, 1, 0, 1, 1, 1, 0], dtype=bool)                       # GAS, EMPTY, OIL, WATER, HONEY
+
+
+def _heavier2(u, l):
+    return (u != STONE) & _YIELDS2[l] & (_RANK2[u] > _RANK2[l])
+
+
+def _rule2(a, b, c, d, coin, coin2):
+    fa = _heavier2(a, c); a, c = _swap(fa, a, c)
+    fb = _heavier2(b, d); b, d = _swap(fb, b, d)
+    da = _heavier2(a, d) & (b != STONE) & (a != GRAVEL)
+    db = _heavier2(b, c) & (a != STONE) & (b != GRAVEL) & ~da
+    a, d = _swap(da, a, d)
+    b, c = _swap(db, b, c)
+    l = (a != b) & _YIELDS2[a] & _YIELDS2[b]
+    viscous = (a == HONEY) | (b == HONEY)
+    a, b = _swap(l & coin & (~viscous | coin2), a, b)
+    return a, b, c, d
+
+
 def _dens(m):
     return np.where(m == SAND, 2, np.where(m == WATER, 1, 0))
 
@@ -70,7 +105,7 @@ def _rule(a, b, c, d, coin):
     return a, b, c, d
 
 
-def _substep(grid, k, axis, oh, oy):
+def _substep(grid, k, axis, oh, oy, version=1):
     """axis 0: XY blocks (horizontal = x, numpy axis 2); axis 1: ZY blocks (horizontal = z, numpy axis 0)."""
     nz, ny, nx = grid.shape
     g = np.transpose(grid, (2, 1, 0)) if axis == 1 else grid     # -> (free, y, h)
@@ -87,11 +122,13 @@ def _substep(grid, k, axis, oh, oy):
     Yu = (np.arange(nby) * 2 + sy + 1 - 1)[None, :, None]
     F = np.arange(nf)[:, None, None]
     H0b, Yub, Fb = np.broadcast_arrays(H0, Yu, F)
-    if axis == 0:
-        coin = coins(k, H0b, Yub, Fb)        # (X, Y, Z) = (h0, y0+1, z)
+    XYZ = (H0b, Yub, Fb) if axis == 0 else (Fb, Yub, H0b)     # XY: (h0, y0+1, z); ZY: (x, y0+1, z0)
+    coin = coins(k, *XYZ)
+    if version == 2:
+        # outside the grid the coordinates are meaningless, but there a or b reads STONE and L cannot fire
+        a2, b2, c2, d2 = _rule2(a, b, c, d, coin, coins2(k, *XYZ))
     else:
-        coin = coins(k, Fb, Yub, H0b)        # (X, Y, Z) = (x, y0+1, z0)
-    a2, b2, c2, d2 = _rule(a, b, c, d, coin)
+        a2, b2, c2, d2 = _rule(a, b, c, d, coin)
     P[:, ys1, hs], P[:, ys1, hs1], P[:, ys, hs], P[:, ys, hs1] = a2, b2, c2, d2
     out = P[:, 1:-1, 1:-1]
     if axis == 1:
@@ -99,16 +136,16 @@ def _substep(grid, k, axis, oh, oy):
     grid[...] = out
 
 
-def step(grid, seed, t):
-    """One in-place step of a whole (nz, ny, nx) uint8 grid."""
+def step(grid, seed, t, version=1):
+    """One in-place step of a whole (nz, ny, nx) uint8 grid under schedule `version` (1: SCHEDULE.md §1-5, 2: §7)."""
     hoff = (t >> 1) & 1
     kxy, kzy = key(seed, t, 0), key(seed, t, 1)
     if t % 2 == 0:
-        _substep(grid, kxy, 0, hoff, 0)
-        _substep(grid, kzy, 1, hoff, 1)
+        _substep(grid, kxy, 0, hoff, 0, version)
+        _substep(grid, kzy, 1, hoff, 1, version)
     else:
-        _substep(grid, kzy, 1, hoff, 0)
-        _substep(grid, kxy, 0, hoff, 1)
+        _substep(grid, kzy, 1, hoff, 0, version)
+        _substep(grid, kxy, 0, hoff, 1, version)
     return grid
 
 
