@@ -348,6 +348,20 @@ static PairLayout pair_layout(const Slab &s, uint32_t oz) {
     return L;
 }
 
+// launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream is
+// still running and waits for it in griddepcontrol.wait (step_kernel.cuh, pdl_wait)
+template <class Param>
+static cudaError_t launch_pdl(void (*kernel)(const Param), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, const Param &arg) {
+    static const bool off = std::getenv("FS3D_NO_PDL") != nullptr;      // A/B switch
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+
 static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns, int push = 0) {
     if (pe <= pb) return FS3D_OK;
     const uint64_t t = w->step;
@@ -412,10 +426,14 @@ static int launch_pairs(fs3d_world *w, Slab &s, uint32_t pb, uint32_t pe, int ns
         q.stats_prev = s.d_stats + 4 * ((k + 2) % 3); q.stats_cur = s.d_stats + 4 * (k % 3); q.stats_next = s.d_stats + 4 * ((k + 1) % 3);
         q.runs = s.d_runs; q.nruns = s.d_nruns + (s.plan_launch & 1); q.nruns_next = s.d_nruns + ((s.plan_launch + 1) & 1);
         s.plan_launch++;
-        skip_plan_kernel<<<(unsigned)((npg + 3) / 4), 128, 0, s.s_main>>>(q);
-        FS3D_CUDA(cudaGetLastError());
+        FS3D_CUDA(launch_pdl(skip_plan_kernel, (unsigned)((npg + 3) / 4), 128, 0, s.s_main, q));
         w->launches++;
         p.runs = q.runs; p.nruns = q.nruns;
+        // the plan and the march are short when most tiles sleep: programmatic dependent launch hides the launch latency
+        FS3D_CUDA(launch_pdl(step_fn(w->version, w->jidx, (int)hoff, (int)todd, sk, ns, push), (unsigned)blocks, (unsigned)threads,
+                             step_smem(w->jidx, push), s.s_main, p));
+        w->launches++;
+        return FS3D_OK;
     }
     step_fn(w->version, w->jidx, (int)hoff, (int)todd, sk, ns, push)<<<(unsigned)blocks, threads, step_smem(w->jidx, push), s.s_main>>>(p);
     FS3D_CUDA(cudaGetLastError());
@@ -1086,7 +1104,7 @@ int fs3d_histogram(fs3d_world *w, uint64_t counts[256]) {
     const size_t pb = plane_bytes(w);
     for (auto &s : w->slabs) {
         FS3D_CUDA(cudaSetDevice(s.device));
-        FS3D_CUDA(cudaMemsetAsync(s.d_scratch, 0, 2512 * sizeof(unsigned long long), s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.d_scratch, 0, 256 * sizeof(unsigned long long), s.s_main));
         uint64_t n16 = pb * s.nzl / 16;
         histogram_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), n16, s.d_scratch);
         FS3D_CUDA(cudaGetLastError());

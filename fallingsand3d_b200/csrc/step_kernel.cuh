@@ -131,6 +131,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// programmatic dependent launch (PDL): used by the settled-tile path, where a pass is two short kernels
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
     // space is cut into equal contiguous ranges, one per resident warp (no tail, one lead-in each).
     // With skipping only the live segments exist as work: skip_plan_kernel compacts them into a list of
     // runs (a few y-blocks of one pair group each) that is dealt round-robin to the warps.
+    if (SKIP) { pdl_launch_dependents(); pdl_wait(); }      // the run list comes from the plan kernel just in front (PDL)
     const uint32_t nruns = SKIP ? *p.nruns : 0xFFFFFFFFu;
     uint32_t run = gw;
     uint64_t pos = total * gw / nw;
@@ -692,6 +696,10 @@ struct PlanParams {
 };
 
 static __global__ void skip_plan_kernel(const PlanParams q) {   // static: step_kernel.cuh is included by two translation units
+    // Programmatic dependent launch (both no-ops in an ordinary launch): let the step kernel behind this one be
+    // scheduled already, and do not read what the step kernel in front of this one wrote before it has completed.
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t npairs = q.pair_end - q.pair_begin;
     const uint32_t npg = (npairs + q.groups - 1) / q.groups;
     const uint32_t blk = 1u << q.blk_log2;
@@ -724,14 +732,21 @@ static __global__ void skip_plan_kernel(const PlanParams q) {   // static: step_
     auto tile_quiet = [&](uint32_t zt, uint32_t yt) -> bool {
         if (q.force_live) return false;
         if ((zt == 0 && q.has_lo_neighbour) || (zt == q.nztiles - 1 && q.has_hi_neighbour)) return false;
+        // newest stamp of the 3 x 3 neighbourhood: nine independent loads (indices clamped into the map — a clamped
+        // index repeats a tile of the neighbourhood, which cannot change the maximum), not a chain of nine
+        uint32_t newest = 0;
+#pragma unroll
         for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
-                const int z = (int)zt + dz, y = (int)yt + dy;
-                if (z < 0 || z >= (int)q.nztiles || y < 0 || y >= (int)q.nytiles) continue;
-                // quiet for steps t_now-4 .. t_now-1  <=>  la (= last active step + 1) + 4 <= t_now
-                if ((uint64_t)q.last_active[(size_t)z * q.nytiles + y] + 4ull > (uint64_t)q.t_now) return false;
+                int z = (int)zt + dz, y = (int)yt + dy;
+                z = z < 0 ? 0 : (z >= (int)q.nztiles ? (int)q.nztiles - 1 : z);
+                y = y < 0 ? 0 : (y >= (int)q.nytiles ? (int)q.nytiles - 1 : y);
+                const uint32_t la = q.last_active[(size_t)z * q.nytiles + y];
+                newest = la > newest ? la : newest;
             }
-        return true;
+        // quiet for steps t_now-4 .. t_now-1  <=>  la (= last active step + 1) + 4 <= t_now
+        return (uint64_t)newest + 4ull <= (uint64_t)q.t_now;
     };
     const uint32_t zmask = (1u << q.ztile_log2) - 1u;
     const uint32_t wpb = blockDim.x >> 5;

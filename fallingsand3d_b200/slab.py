@@ -330,11 +330,21 @@ class SlabWorld:
             dist.broadcast_object_list(blob, src=0, group=self.group)
             w.frame_attach(blob[0], self.rank)
             self._frame_dims = (width, height)
+        import time
+        t0 = time.perf_counter()
         dist.barrier(group=self.group)          # rank 0 has resolved the previous frame: slots may be overwritten
+        t1 = time.perf_counter()
         w.raymarch_to_frame(**cam)
         w.sync()
+        t2 = time.perf_counter()
         dist.barrier(group=self.group)          # every slot is complete
-        return w.frame_resolve(width, height) if self.rank == 0 else None
+        t3 = time.perf_counter()
+        img = w.frame_resolve(width, height) if self.rank == 0 else None
+        t4 = time.perf_counter()
+        # where a frame's wall time goes on this rank (ms): tools/run_configs.py config 5 reports rank 0's
+        self.last_frame_ms = {"barrier_before": (t1 - t0) * 1e3, "march_kernel_and_sync": (t2 - t1) * 1e3,
+                              "barrier_after": (t3 - t2) * 1e3, "resolve_and_d2h": (t4 - t3) * 1e3}
+        return img
 
     def close(self):
         self.engine.close()

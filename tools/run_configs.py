@@ -145,6 +145,7 @@ def config5():
     dist.barrier()
     t0 = time.perf_counter()
     rm = []
+    phases = []
     img = None
     for k in range(6):
         sw.step(10)
@@ -152,6 +153,7 @@ def config5():
         t1 = time.perf_counter()
         img = sw.raymarch(**cam)
         rm.append(time.perf_counter() - t1)
+        phases.append(dict(getattr(sw, "last_frame_ms", {})))
     sw.sync()
     dist.barrier()
     wall = time.perf_counter() - t0
@@ -160,7 +162,7 @@ def config5():
     if rank == 0:
         res = {"config": f"{n}^3 random fill on {sw.world_size} GPUs, raymarch 1920x1080 every 10 steps",
                "ms_per_step_stepping_only": ms_step, "voxel_updates_per_s": n ** 3 / (ms_step * 1e-3),
-               "wall_s_60_steps_with_6_frames": wall, "raymarch_ms_per_frame_incl_gather": [1e3 * r for r in rm],
+               "wall_s_60_steps_with_6_frames": wall, "raymarch_ms_per_frame_incl_gather": [1e3 * r for r in rm], "raymarch_phases_ms_rank0": phases,
                "image_nonblack_pixels": int((img[..., :3].sum(axis=-1) > 0).sum()), "histogram_invariant": ok,
                "digest": hex(sw.digest())}
     else:
