@@ -66,6 +66,7 @@ SIGNATURES = {
     "fs3d_volume_export_fd": (C.c_int, [_W, C.c_int32, C.POINTER(Export)]),
     "fs3d_set_palette": (C.c_int, [_W, C.POINTER(C.c_float)]),
     "fs3d_raymarch": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "fs3d_raymarch_bricks_in_use": (C.c_int, [_W, C.c_int32]),
     "fs3d_raymarch_depth": (C.c_int, [_W, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "fs3d_slab_halo": (C.c_int, [_W, C.c_int, C.POINTER(Halo)]),
     "fs3d_slab_pass_steps": (C.c_int, [_W, C.c_uint32]),

@@ -50,6 +50,11 @@ struct Slab {
     float *d_palette = nullptr;
     float *d_thr = nullptr;          // 256 sRGB thresholds (ray-march of this slab into a frame slot)
     bool palette_current = false;    // d_palette holds the world's palette
+    // ray-march empty-space skipping: occupancy bits of this slab's 8^3 bricks, valid for content epoch bricks_epoch
+    uint32_t *d_bricks = nullptr; size_t bricks_bytes = 0; uint64_t bricks_epoch = ~0ull;
+    unsigned long long *d_rm_steps = nullptr;   // loop iterations of the last frame's rays on this slab
+    bool rm_bricks_on = false;                  // last decision (hysteresis)
+    uint64_t rm_pixels = 0;                     // rays of the last frame
     int num_sms = 0;
     int blocks_per_sm[2][2][2][2][2] = {};   // [PUSH][NS-1][SKIP][OX][TODD] for this world's J
     // fused halo push (one process per GPU, CUDA IPC): my arrival counters and the neighbours' memory
@@ -99,6 +104,7 @@ struct fs3d_world {
     unsigned long long push_timeout_ns = 20000ull * 1000000ull;   // watchdog of the fused halo push (FS3D_PUSH_TIMEOUT_MS)
     int version = 1;             // schedule version: 1 (four materials) or 2 (FS3D_FLAG_MATERIALS8: eight, SCHEDULE.md §7)
     uint8_t max_material = FS3D_STONE;
+    uint64_t content_epoch = 0;  // bumps whenever cells may have changed (steps, edits): the ray-marcher's brick maps follow it
     bool force_live = false;     // fs3d_step_host in flight: settled-tile plans treat every tile as live
     bool failed = false;         // the watchdog fired: cells are undefined, stepping is refused
 };
@@ -297,6 +303,8 @@ static void free_slab(Slab &s) {
     if (s.d_img) cudaFree(s.d_img);
     if (s.d_palette) cudaFree(s.d_palette);
     if (s.d_thr) cudaFree(s.d_thr);
+    if (s.d_bricks) cudaFree(s.d_bricks);
+    if (s.d_rm_steps) cudaFree(s.d_rm_steps);
     if (s.d_last_active) cudaFree(s.d_last_active);
     if (s.d_stats) cudaFree(s.d_stats);
     if (s.d_runs) cudaFree(s.d_runs);
@@ -451,6 +459,7 @@ static int launch_skip_map(fs3d_world *, Slab &s) {
 // after the front buffer was edited from outside the step (upload / generate / set_cell / fill_box):
 // every tile counts as active "just now", so the next four steps run everywhere
 static int touch_all_tiles(fs3d_world *w) {
+    w->content_epoch++;
     for (auto &s : w->slabs) {
         if (!s.d_last_active) continue;
         FS3D_CUDA(cudaSetDevice(s.device));
@@ -543,6 +552,7 @@ static int step_pass(fs3d_world *w, int ns) {
     }
     w->cur ^= 1;
     w->step += (uint64_t)ns;
+    w->content_epoch++;
     return FS3D_OK;
 }
 
@@ -642,6 +652,48 @@ static int ensure_frame(Slab &s, uint32_t width, uint32_t height, uint32_t n_slo
     return FS3D_OK;
 }
 
+// Empty-space skipping of one slab for the frame about to be marched.  Whether bricks pay is decided from the previous
+// frame on this slab: without bricks, more than 48 loop iterations per ray means rays cross a lot of air; with bricks,
+// fewer than 8 means they hit at once anyway (the map costs one read of the slab).  Returns the device pointer or
+// nullptr, and resets the step counter.  The slab's stream must be idle or ordered (it is: frames are synchronous
+// per slab).
+static int prepare_bricks(fs3d_world *w, Slab &s, uint32_t mode, uint64_t pixels, const uint32_t **out) {
+    *out = nullptr;
+    FS3D_CUDA(cudaSetDevice(s.device));
+    if (!s.d_rm_steps) {
+        FS3D_CUDA(cudaMalloc(&s.d_rm_steps, sizeof(unsigned long long)));
+        FS3D_CUDA(cudaMemsetAsync(s.d_rm_steps, 0, sizeof(unsigned long long), s.s_main));
+    }
+    unsigned long long steps = 0;
+    FS3D_CUDA(cudaMemcpyAsync(&steps, s.d_rm_steps, sizeof(steps), cudaMemcpyDeviceToHost, s.s_main));
+    FS3D_CUDA(cudaStreamSynchronize(s.s_main));
+    FS3D_CUDA(cudaMemsetAsync(s.d_rm_steps, 0, sizeof(unsigned long long), s.s_main));
+    const double per_ray = s.rm_pixels ? (double)steps / (double)s.rm_pixels : 0.0;
+    s.rm_pixels = pixels;
+    bool on = s.rm_bricks_on ? per_ray > 8.0 : per_ray > 48.0;
+    if (mode & FS3D_RM_BRICKS) on = true;
+    if (mode & FS3D_RM_NO_BRICKS) on = false;
+    s.rm_bricks_on = on;
+    if (!on) return FS3D_OK;
+    const size_t bytes = brick_words(w->desc.nx, w->desc.ny, s.z0, s.z0 + s.nzl) * sizeof(uint32_t);
+    if (s.bricks_bytes < bytes) {
+        if (s.d_bricks) cudaFree(s.d_bricks);
+        s.d_bricks = nullptr; s.bricks_bytes = 0;
+        FS3D_CUDA(cudaMalloc(&s.d_bricks, bytes));
+        s.bricks_bytes = bytes;
+        s.bricks_epoch = ~0ull;
+    }
+    if (s.bricks_epoch != w->content_epoch) {
+        const uint64_t warps = bytes / 16;       // one warp per 128 bricks
+        brick_build_kernel<<<grid_for(warps * 32, s), 256, 0, s.s_main>>>(owned_ptr(w, s, w->cur), w->desc.nx, w->desc.ny, s.z0, s.z0 + s.nzl, s.d_bricks);
+        FS3D_CUDA(cudaGetLastError());
+        w->launches++;
+        s.bricks_epoch = w->content_epoch;
+    }
+    *out = s.d_bricks;
+    return FS3D_OK;
+}
+
 // march one slab of the world on its own device into `frame_slot` (asynchronous on the slab's stream)
 static int raymarch_slab_to_frame(fs3d_world *w, Slab &s, const fs3d_camera *cam, uint32_t width, uint32_t height,
                                   uint32_t mode, unsigned long long *frame_slot) {
@@ -655,6 +707,9 @@ static int raymarch_slab_to_frame(fs3d_world *w, Slab &s, const fs3d_camera *cam
     p.nslabs = 1;
     p.slab_ptr[0] = owned_ptr(w, s, w->cur);
     p.slab_z0[0] = s.z0; p.slab_z1[0] = s.z0 + s.nzl;
+    p.zheld0 = s.z0; p.zheld1 = s.z0 + s.nzl;
+    if ((mode & 15u) == FS3D_RM_VOXELS) { int rc = prepare_bricks(w, s, mode, (uint64_t)width * height, &p.bricks[0]); if (rc) return rc; }
+    p.steps_out = s.d_rm_steps;
     p.palette = s.d_palette;
     if (mode & FS3D_RM_SRGB) {
         float thr[256];
@@ -747,6 +802,23 @@ int raymarch_world(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32
         p.slab_z0[i] = w->slabs[i].z0;
         p.slab_z1[i] = w->slabs[i].z0 + w->slabs[i].nzl;
     }
+    p.zheld0 = w->slabs.front().z0; p.zheld1 = w->slabs.back().z0 + w->slabs.back().nzl;
+    // bricks only where the marching device owns the slab (peer-read slabs march voxel by voxel); the decision is s0's
+    if ((mode & 15u) == FS3D_RM_VOXELS) {
+        int rc = prepare_bricks(w, s0, mode, (uint64_t)npix, &p.bricks[0]);
+        if (rc) return rc;
+        for (int i = 1; i < p.nslabs; ++i) {
+            p.bricks[i] = nullptr;
+            if (w->slabs[i].device != s0.device || p.bricks[0] == nullptr) continue;
+            const uint32_t *b = nullptr;
+            rc = prepare_bricks(w, w->slabs[i], mode | FS3D_RM_BRICKS, (uint64_t)npix, &b);
+            if (rc) return rc;
+            FS3D_CUDA(cudaStreamSynchronize(w->slabs[i].s_main));      // built on that slab's stream, read on s0's
+            p.bricks[i] = b;
+        }
+        FS3D_CUDA(cudaSetDevice(s0.device));
+    }
+    p.steps_out = s0.d_rm_steps;
     p.palette = s0.d_palette;
     p.srgb_thr = nullptr;
     if (mode & FS3D_RM_SRGB) {
@@ -1214,6 +1286,11 @@ int fs3d_set_palette(fs3d_world *w, const float *rgba256x4) {
     return FS3D_OK;
 }
 
+int fs3d_raymarch_bricks_in_use(fs3d_world *w, int32_t slab) {
+    if (!w || slab < 0 || slab >= (int32_t)w->slabs.size()) return 0;
+    return w->slabs[slab].rm_bricks_on ? 1 : 0;
+}
+
 int fs3d_raymarch(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height, uint32_t mode, uint8_t *host_rgba8) {
     if (!w || !cam || !host_rgba8) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
     if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(FS3D_ERR_INVALID_ARG, "bad image size");
@@ -1280,6 +1357,7 @@ int fs3d_slab_step_finish(fs3d_world *w) {
     if (w->edges_phase != 2) return fail(FS3D_ERR_INVALID_ARG, "call fs3d_slab_step_interior first");
     w->cur ^= 1;
     w->step += (uint64_t)w->pass_ns;
+    w->content_epoch++;
     w->edges_phase = 0;
     return FS3D_OK;
 }

@@ -9,9 +9,11 @@
 //   /root/reference/src/engine/rendering/renderer.cpp:1253-1267  quad UVs: pixel centre (px,py) ->
 //        u = 1 - (px+.5)/W, v = (py+.5)/H  (x mirrored; Vulkan NDC y down)
 // Mode FS3D_RM_SDF_SPHERE reproduces the shader as shipped (analytic sphere, no volume input).
-// Mode FS3D_RM_VOXELS keeps camera + light and replaces map_the_world by an Amanatides-Woo DDA
+// Mode FS3D_RM_VOXELS keeps camera + light and replaces map_the_world by an Amanatides-Woo walk
 // through the uint8 grid with a 256-entry palette (the reference's unused colors[256],
-// renderer.cpp:136-393, is the intended shape of that palette).
+// renderer.cpp:136-393, is the intended shape of that palette).  Crossing times are recomputed from the integer
+// boundary index (boundary_t) rather than accumulated, which makes the walk's state a function of position alone; the
+// kernel uses that to jump over empty 8^3 bricks and over planes held by other ranks in one move, exactly.
 //
 // Every float operation is an explicit round-to-nearest intrinsic in a fixed order (no FMA
 // contraction), so the image is bit-identical to oracle/fs3d_raymarch_oracle.c.
@@ -42,6 +44,9 @@ struct RMParams {
     float *depth;            // W*H hit parameter t (inf on miss), may be nullptr
     unsigned long long *frame;   // non-null: store (float bits of t) << 32 | rgba8 per pixel here instead (this
                                  // rank's slot of the compositor's frame, possibly peer memory over NVLink)
+    uint32_t zheld0, zheld1;     // union of the slabs' plane ranges: rays jump over the planes outside it in one move
+    const uint32_t *bricks[RM_MAX_SLABS];    // per slab: occupancy bits of its 8 x 8 x 8 bricks (nullptr: not built, march every voxel)
+    unsigned long long *steps_out;           // += loop iterations of every ray (the host decides from it whether bricks pay)
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -79,12 +84,57 @@ __device__ __forceinline__ uint8_t encode8(float v, const float *thr) {
     return (uint8_t)(int)fadd(fmul(v, 255.0f), 0.5f);
 }
 
-__device__ __forceinline__ uint8_t voxel_at(const RMParams &p, int ix, int iy, int iz) {
-#pragma unroll 1
-    for (int s = 0; s < p.nslabs; ++s)
-        if ((uint32_t)iz >= p.slab_z0[s] && (uint32_t)iz < p.slab_z1[s])
-            return p.slab_ptr[s][(size_t)ix + (size_t)p.nx * ((size_t)iy + (size_t)p.ny * ((size_t)iz - p.slab_z0[s]))];
-    return 0;   // plane not held by this rank: transparent (composited by depth across ranks)
+// ---- empty-space skipping ------------------------------------------------------------------------------------------
+// Occupancy of 8 x 8 x 8 bricks (grid coordinates, z bricks aligned to global z), one bit each.  A warp of the build
+// kernel takes one (brick row y, brick layer z) of one 1024-voxel x segment: lane l ORs the 32-byte words
+// x in [32 l, 32 l + 32) of the brick's (up to) 64 rows — four bricks per lane — and four ballots store the segment's
+// 128 bits: brick r = 4 l + k of the segment sits in word k, bit l.
+__host__ __device__ inline size_t brick_word(uint32_t nbx, uint32_t nby, uint32_t bx, uint32_t by, uint32_t bzl) {
+    const uint32_t nseg = (nbx + 127u) >> 7;
+    return (((size_t)bzl * nby + by) * nseg + (bx >> 7)) * 4u + (bx & 3u);
+}
+__host__ __device__ inline uint32_t brick_bit(uint32_t bx) { return (bx & 127u) >> 2; }
+inline size_t brick_words(uint32_t nx, uint32_t ny, uint32_t z0, uint32_t z1) {
+    const uint32_t nbx = nx / 8, nby = (ny + 7) / 8, nbz = ((z1 + 7) >> 3) - (z0 >> 3);
+    return (size_t)nbz * nby * ((nbx + 127u) >> 7) * 4u;
+}
+__global__ void brick_build_kernel(const uint8_t *owned, uint32_t nx, uint32_t ny, uint32_t z0, uint32_t z1, uint32_t *bricks) {
+    const uint32_t nbx = nx / 8, nby = (ny + 7) / 8, nbz = ((z1 + 7) >> 3) - (z0 >> 3), nseg = (nbx + 127u) >> 7;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nwork = (uint64_t)nbz * nby * nseg;
+    for (uint64_t wk = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5; wk < nwork; wk += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+        const uint32_t seg = (uint32_t)(wk % nseg), by = (uint32_t)((wk / nseg) % nby), bzl = (uint32_t)(wk / ((uint64_t)nseg * nby));
+        const uint32_t xw = seg * 32u + lane;                       // 32-voxel word of the row
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};                         // OR of bytes [8k, 8k + 8) of the word over the brick's rows
+        if (xw * 32u < nx) {
+            const uint32_t zb = ((z0 >> 3) + bzl) << 3;
+            for (uint32_t dz = 0; dz < 8u; ++dz) {
+                const uint32_t z = zb + dz;
+                if (z < z0 || z >= z1) continue;
+                for (uint32_t dy = 0; dy < 8u; ++dy) {
+                    const uint32_t y = by * 8u + dy;
+                    if (y >= ny) break;
+                    const uint4 *q = reinterpret_cast<const uint4 *>(owned + ((size_t)(z - z0) * ny + y) * nx + (size_t)xw * 32u);
+                    const uint4 a = q[0], b = q[1];
+                    acc[0] |= a.x | a.y; acc[1] |= a.z | a.w; acc[2] |= b.x | b.y; acc[3] |= b.z | b.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, acc[k] != 0u);
+            if (lane == 0) bricks[(((size_t)bzl * nby + by) * nseg + seg) * 4u + k] = bits;
+        }
+    }
+}
+
+// crossing time of lattice boundary k on axis a: ((k h - e) - o) * (1 / d), every operation rounded separately.  The
+// walk below recomputes it from the integer boundary index after every move instead of accumulating t += dt, so the
+// state of a ray depends only on WHERE it is, not on how it got there — which is what makes jumping over empty
+// bricks (and over the planes another rank holds) exact: after a jump the ray is in the very state the
+// voxel-by-voxel walk would have reached (oracle/fs3d_raymarch_oracle.c walks voxel by voxel and must agree).
+__device__ __forceinline__ float boundary_t(int k, float h, float e, float o, float rcp) {
+    return fmul(fsub(fsub(fmul((float)k, h), e), o), rcp);
 }
 
 __global__ void raymarch_kernel(const RMParams p) {
@@ -107,6 +157,7 @@ __global__ void raymarch_kernel(const RMParams p) {
     }
 
     float r = 0.f, g = 0.f, b = 0.f, depth = INFINITY;
+    uint32_t nsteps = 0;                 // loop iterations of this ray's walk (voxel moves + jumps)
 
     if ((p.mode & 15u) == FS3D_RM_SDF_SPHERE) {
         float t = 0.0f;
@@ -149,7 +200,7 @@ __global__ void raymarch_kernel(const RMParams p) {
             // entry point in lattice units along each axis (world axis direction, not grid y)
             const int n[3] = {(int)p.nx, (int)p.ny, (int)p.nz};
             int idx[3], stp[3];
-            float tnext[3], tdelta[3];
+            float tnext[3], rcp[3];
             int last_axis = -1;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
@@ -159,17 +210,9 @@ __global__ void raymarch_kernel(const RMParams p) {
                 if (i < 0) i = 0;
                 if (i > n[a] - 1) i = n[a] - 1;
                 idx[a] = i;
-                if (d[a] > 0.0f) {
-                    stp[a] = 1;
-                    tnext[a] = fdiv(fsub(fsub(fmul((float)(i + 1), p.h), e[a]), o[a]), d[a]);
-                    tdelta[a] = fdiv(p.h, d[a]);
-                } else if (d[a] < 0.0f) {
-                    stp[a] = -1;
-                    tnext[a] = fdiv(fsub(fsub(fmul((float)i, p.h), e[a]), o[a]), d[a]);
-                    tdelta[a] = fdiv(p.h, -d[a]);
-                } else {
-                    stp[a] = 0; tnext[a] = INFINITY; tdelta[a] = INFINITY;
-                }
+                stp[a] = d[a] > 0.0f ? 1 : (d[a] < 0.0f ? -1 : 0);
+                rcp[a] = stp[a] != 0 ? fdiv(1.0f, d[a]) : 0.0f;
+                tnext[a] = stp[a] != 0 ? boundary_t(i + (stp[a] > 0 ? 1 : 0), p.h, e[a], o[a], rcp[a]) : INFINITY;
             }
             // which face did we enter through?  the axis whose slab entry time equals tmin
             {
@@ -184,9 +227,79 @@ __global__ void raymarch_kernel(const RMParams p) {
                 }
             }
             float t = tmin;
+            // Jump out of an empty axis-aligned box lo <= idx < hi (lattice coordinates) in ONE move, landing in exactly
+            // the state the voxel-by-voxel walk reaches when it leaves the box: the exit event is the earliest crossing of
+            // a box face (ties: lowest axis, like the walk's choice of axis); on the other axes every lattice boundary is
+            // crossed whose time is earlier — or equal, on a lower axis — found from the exit point and corrected with
+            // the same boundary_t comparisons the walk makes.  Returns false if the ray leaves the grid.
+            auto jump = [&](const int (&lo)[3], const int (&hi)[3]) -> bool {
+                float tex[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    tex[a] = stp[a] != 0 ? boundary_t(stp[a] > 0 ? hi[a] : lo[a], p.h, e[a], o[a], rcp[a]) : INFINITY;
+                int ax = 0;
+                if (tex[1] < tex[ax]) ax = 1;
+                if (tex[2] < tex[ax]) ax = 2;
+                const float T = tex[ax];
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    if (b == ax) { idx[b] = stp[b] > 0 ? hi[b] : lo[b] - 1; continue; }
+                    if (stp[b] == 0) continue;
+                    auto crossed = [&](int k) { const float tb = boundary_t(k, p.h, e[b], o[b], rcp[b]); return tb < T || (tb == T && b < ax); };
+                    int g = (int)floorf(fdiv(fadd(fadd(o[b], fmul(T, d[b])), e[b]), p.h));
+                    if (stp[b] > 0) {          // moving up crosses boundary i to enter voxel i
+                        g = g < idx[b] ? idx[b] : (g > hi[b] - 1 ? hi[b] - 1 : g);
+                        while (g > idx[b] && !crossed(g)) --g;
+                        while (g + 1 <= hi[b] - 1 && crossed(g + 1)) ++g;
+                    } else {                   // moving down crosses boundary i to leave voxel i
+                        g = g > idx[b] ? idx[b] : (g < lo[b] ? lo[b] : g);
+                        while (g < idx[b] && !crossed(g + 1)) ++g;
+                        while (g - 1 >= lo[b] && crossed(g)) --g;
+                    }
+                    idx[b] = g;
+                }
+                if (idx[ax] < 0 || idx[ax] >= n[ax]) return false;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    if (stp[a] != 0) tnext[a] = boundary_t(idx[a] + (stp[a] > 0 ? 1 : 0), p.h, e[a], o[a], rcp[a]);
+                t = T;
+                last_axis = ax;
+                return true;
+            };
             const int max_steps = n[0] + n[1] + n[2] + 3;
-            for (int s = 0; s < max_steps; ++s) {
-                uint8_t m = voxel_at(p, idx[0], n[1] - 1 - idx[1], idx[2]);
+            uint32_t cbx = 0xFFFFFFFFu, cby = 0xFFFFFFFFu, cbz = 0xFFFFFFFFu;     // brick whose occupancy bit is cached
+            bool cached_occ = true;
+            int s = 0;
+            for (; s < max_steps; ++s) {
+                const int gx = idx[0], gy = n[1] - 1 - idx[1], gz = idx[2];
+                if ((uint32_t)gz < p.zheld0 || (uint32_t)gz >= p.zheld1) {
+                    // planes no slab of this launch holds (another rank's): transparent here — cross them in one move
+                    const int lo[3] = {0, 0, (uint32_t)gz < p.zheld0 ? 0 : (int)p.zheld1};
+                    const int hi[3] = {n[0], n[1], (uint32_t)gz < p.zheld0 ? (int)p.zheld0 : n[2]};
+                    if (!jump(lo, hi)) break;
+                    continue;
+                }
+                int sl = 0;
+#pragma unroll 1
+                for (int q = 0; q < p.nslabs; ++q) if ((uint32_t)gz >= p.slab_z0[q] && (uint32_t)gz < p.slab_z1[q]) sl = q;
+                if (p.bricks[sl] != nullptr) {
+                    const uint32_t bx = (uint32_t)gx >> 3, by = (uint32_t)gy >> 3, bz = (uint32_t)gz >> 3;
+                    if (bx != cbx || by != cby || bz != cbz) {
+                        cbx = bx; cby = by; cbz = bz;
+                        const uint32_t nbx = p.nx >> 3, nby = (p.ny + 7u) >> 3;
+                        cached_occ = (p.bricks[sl][brick_word(nbx, nby, bx, by, bz - (p.slab_z0[sl] >> 3))] >> brick_bit(bx)) & 1u;
+                    }
+                    if (!cached_occ) {
+                        // the brick (clipped to the slab's planes) in lattice coordinates: grid rows [8 by, 8 by + 8) are
+                        // lattice rows [ny - 8 by - 8, ny - 8 by)
+                        const int zlo = max((int)(bz << 3), (int)p.slab_z0[sl]), zhi = min((int)(bz << 3) + 8, (int)p.slab_z1[sl]);
+                        const int lo[3] = {(int)(bx << 3), max(0, n[1] - (int)(by << 3) - 8), zlo};
+                        const int hi[3] = {(int)(bx << 3) + 8, n[1] - (int)(by << 3), zhi};
+                        if (!jump(lo, hi)) break;
+                        continue;
+                    }
+                }
+                const uint8_t m = p.slab_ptr[sl][(size_t)gx + (size_t)p.nx * ((size_t)gy + (size_t)p.ny * ((size_t)gz - p.slab_z0[sl]))];
                 if (m != 0) {
                     float nrm[3] = {0.f, 0.f, 0.f};
                     if (last_axis >= 0) nrm[last_axis] = stp[last_axis] > 0 ? -1.0f : 1.0f;
@@ -203,12 +316,18 @@ __global__ void raymarch_kernel(const RMParams p) {
                 t = tnext[a];
                 idx[a] += stp[a];
                 if (idx[a] < 0 || idx[a] >= n[a]) break;
-                tnext[a] = fadd(tnext[a], tdelta[a]);
+                tnext[a] = boundary_t(idx[a] + (stp[a] > 0 ? 1 : 0), p.h, e[a], o[a], rcp[a]);
                 last_axis = a;
             }
+            nsteps = (uint32_t)s;
         }
     }
 
+    if (p.steps_out) {                   // one atomic per warp (warps at the image edge are partial)
+        const unsigned act = __activemask();
+        const uint32_t sum = __reduce_add_sync(act, nsteps);
+        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(p.steps_out, (unsigned long long)sum);
+    }
     const size_t pix = (size_t)py * p.W + px;
     if (p.frame) {
         // t >= 0, so its bit pattern orders like the float: the compositor takes the 64-bit minimum over ranks

@@ -24,6 +24,7 @@ FLAG_PEER_PUSH_SHARED_DEVICE = 8
 FLAG_EXPORTABLE = 16
 FLAG_MATERIALS8 = 32
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
+RM_BRICKS, RM_NO_BRICKS = 32, 64      # force / forbid the 8^3-brick empty-space skipping (default: adaptive; same image)
 
 ERROR_NAMES = {-1: "INVALID_ARG", -2: "BAD_DIMS", -3: "BAD_MATERIAL", -4: "OUT_OF_RANGE", -5: "CUDA",
                -6: "OOM", -7: "UNSUPPORTED", -8: "IO"}
@@ -225,6 +226,9 @@ class VoxelWorld:
             return img, depth
         _check(self._lib.fs3d_raymarch(self._h, C.byref(cam), width, height, mode, img.ctypes.data_as(C.c_void_p)))
         return img
+
+    def raymarch_bricks_in_use(self, slab=0):
+        return bool(self._lib.fs3d_raymarch_bricks_in_use(self._h, int(slab)))
 
     # ---- fused multi-rank ray-march (see slab.SlabWorld.raymarch) ----
     def frame_export(self, width, height, n_slots):

@@ -142,6 +142,9 @@ typedef struct {
 #define FS3D_RM_SDF_SPHERE 0   /* fs_raymarch.frag as shipped: analytic sphere r=0.5 at origin */
 #define FS3D_RM_VOXELS     1   /* same camera/light, voxel DDA through the grid + palette */
 #define FS3D_RM_SRGB       16  /* OR-able: sRGB-encode like the reference's B8G8R8A8_SRGB swapchain */
+#define FS3D_RM_BRICKS     32  /* OR-able: always (re)build the 8^3-brick occupancy map and skip empty bricks */
+#define FS3D_RM_NO_BRICKS  64  /* OR-able: never; default: decided from the previous frame's steps per ray.  The image
+                                  is identical either way (the jumps are exact). */
 
 /* Device pointers for an external (one-process-per-GPU) halo exchange; see fs3d_create_slab. */
 typedef struct {
@@ -208,6 +211,8 @@ int  fs3d_volume_export_fd(fs3d_world *w, int32_t slab, fs3d_export *out);   /* 
 int  fs3d_set_palette(fs3d_world *w, const float *rgba256x4);
 int  fs3d_raymarch(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height,
                    uint32_t mode, uint8_t *host_rgba8);
+/* 1 if the last voxel-mode frame marched on `slab` used the brick occupancy map (adaptive unless forced by the mode) */
+int  fs3d_raymarch_bricks_in_use(fs3d_world *w, int32_t slab);
 /* Same, plus the hit parameter t per pixel (+inf on a miss): ranks that each hold one slab
  * composite their images by taking, per pixel, the colour with the smallest t. */
 int  fs3d_raymarch_depth(fs3d_world *w, const fs3d_camera *cam, uint32_t width, uint32_t height,

@@ -76,17 +76,18 @@ void main() {
 	}
 
 	if (!miss && tmin <= tmax) {
+		// crossing times come from the integer boundary index, ((k h - e) - o) * (1 / d): never accumulated (raymarch.cuh)
 		ivec3 idx, stp;
-		vec3 tnext, tdelta;
+		vec3 tnext, rcp;
 		int last_axis = -1;
 		float best = -1.0;
 		for (int a = 0; a < 3; ++a) {
 			float pos = o[a] + tmin * d[a];
 			int i = clamp(int(floor((pos + e[a]) / h)), 0, n[a] - 1);
 			idx[a] = i;
-			if (d[a] > 0.0) { stp[a] = 1; tnext[a] = ((float(i + 1) * h - e[a]) - o[a]) / d[a]; tdelta[a] = h / d[a]; }
-			else if (d[a] < 0.0) { stp[a] = -1; tnext[a] = ((float(i) * h - e[a]) - o[a]) / d[a]; tdelta[a] = h / -d[a]; }
-			else { stp[a] = 0; tnext[a] = 1.0 / 0.0; tdelta[a] = 1.0 / 0.0; }
+			stp[a] = d[a] > 0.0 ? 1 : (d[a] < 0.0 ? -1 : 0);
+			rcp[a] = stp[a] != 0 ? 1.0 / d[a] : 0.0;
+			tnext[a] = stp[a] != 0 ? ((float(i + (stp[a] > 0 ? 1 : 0)) * h - e[a]) - o[a]) * rcp[a] : 1.0 / 0.0;
 			if (d[a] != 0.0) {              // the face the ray entered through: the axis whose slab entry time is tmin
 				float t0 = (-e[a] - o[a]) / d[a], t1 = (e[a] - o[a]) / d[a];
 				float tn = min(t0, t1);
@@ -109,7 +110,7 @@ void main() {
 			t = tnext[a];
 			idx[a] += stp[a];
 			if (idx[a] < 0 || idx[a] >= n[a]) break;
-			tnext[a] += tdelta[a];
+			tnext[a] = ((float(idx[a] + (stp[a] > 0 ? 1 : 0)) * h - e[a]) - o[a]) * rcp[a];
 			last_axis = a;
 		}
 	}

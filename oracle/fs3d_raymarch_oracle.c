@@ -39,6 +39,11 @@ static float diffuse_at(float px, float py, float pz, float nx, float ny, float 
     return d > 0.05f ? d : 0.05f;
 }
 
+/* crossing time of lattice boundary k: ((k h - e) - o) * (1 / d) */
+static float boundary_t(int k, float h, float e, float o, float rcp) {
+    float v = (float)k * h; v = v - e; v = v - o; return v * rcp;
+}
+
 void fs3d_oracle_srgb_thresholds(float *thr /* 256 */) {
     for (int i = 1; i <= 255; ++i) {
         double c = (i - 0.5) / 255.0;
@@ -133,8 +138,12 @@ void fs3d_oracle_raymarch(const uint8_t *grid, uint32_t nx, uint32_t ny, uint32_
                     }
                 }
                 if (!miss && tmin <= tmax) {
+                    /* The walk visits voxel after voxel.  The time at which the ray crosses lattice boundary k of axis a is
+                     * computed from k itself — ((k h - e) - o) * (1 / d), each operation rounded separately — not accumulated,
+                     * so a ray's state is a function of where it is.  (The CUDA kernel relies on that to jump over empty
+                     * bricks and other ranks' planes; this oracle never jumps, and the two must still agree bit for bit.) */
                     int idx[3], stp[3], last_axis = -1;
-                    float tnext[3], tdelta[3];
+                    float tnext[3], rcp[3];
                     for (int a = 0; a < 3; ++a) {
                         float p0 = o[a] + tmin * d[a];
                         float f = (p0 + e[a]) / h;
@@ -142,17 +151,9 @@ void fs3d_oracle_raymarch(const uint8_t *grid, uint32_t nx, uint32_t ny, uint32_
                         if (i < 0) i = 0;
                         if (i > n[a] - 1) i = n[a] - 1;
                         idx[a] = i;
-                        if (d[a] > 0.0f) {
-                            stp[a] = 1;
-                            tnext[a] = (((float)(i + 1) * h - e[a]) - o[a]) / d[a];
-                            tdelta[a] = h / d[a];
-                        } else if (d[a] < 0.0f) {
-                            stp[a] = -1;
-                            tnext[a] = (((float)i * h - e[a]) - o[a]) / d[a];
-                            tdelta[a] = h / -d[a];
-                        } else {
-                            stp[a] = 0; tnext[a] = INFINITY; tdelta[a] = INFINITY;
-                        }
+                        stp[a] = d[a] > 0.0f ? 1 : (d[a] < 0.0f ? -1 : 0);
+                        rcp[a] = stp[a] != 0 ? 1.0f / d[a] : 0.0f;
+                        tnext[a] = stp[a] != 0 ? boundary_t(i + (stp[a] > 0 ? 1 : 0), h, e[a], o[a], rcp[a]) : INFINITY;
                     }
                     {
                         float best = -1.0f;
@@ -186,7 +187,7 @@ void fs3d_oracle_raymarch(const uint8_t *grid, uint32_t nx, uint32_t ny, uint32_
                         t = tnext[a];
                         idx[a] += stp[a];
                         if (idx[a] < 0 || idx[a] >= n[a]) break;
-                        tnext[a] = tnext[a] + tdelta[a];
+                        tnext[a] = boundary_t(idx[a] + (stp[a] > 0 ? 1 : 0), h, e[a], o[a], rcp[a]);
                         last_axis = a;
                     }
                 }

@@ -166,3 +166,77 @@ def test_cuda_voxel_dda_agrees_with_float64_sampling(fs3d, oracle):
             check_sampled_rays(render, oracle, g, cam, 160, 90)
     finally:
         w.close()
+
+
+# ---- empty-space skipping: jumps over empty 8^3 bricks and over other ranks' planes must not change a single bit ----
+CAMS = [dict(pos=(0.0, 0.0, -1.6), aspect=16.0 / 9.0), dict(pos=(0.3, -0.25, -1.2), aspect=1.5, yaw_deg=17.0),
+        dict(pos=(-0.9, 0.2, -0.9), aspect=1.0, yaw_deg=40.0), dict(pos=(0.05, 0.9, -0.2), aspect=1.0, yaw_deg=3.0),
+        dict(pos=(0.0, 0.0, 0.0), aspect=1.3, yaw_deg=180.0)]       # the last one sits inside the volume, looking back
+
+
+@pytest.mark.parametrize("dims,scene", [((64, 48, 40), 2), ((96, 100, 72), 1), ((64, 40, 30), 3), ((256, 60, 36), 4), ((32, 9, 5), 3)])
+def test_brick_skipping_is_exact(fs3d, oracle, dims, scene):
+    nx, ny, nz = dims
+    g = oracle.generate(nx, ny, nz, scene, 3)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=1) as w:
+        w.upload(g)
+        for k, cam in enumerate(CAMS):
+            ref, rdepth = oracle.raymarch(g, width=160, height=90, mode=1, with_depth=True, **cam)
+            for mode in (fs3d.RM_VOXELS | fs3d.RM_BRICKS, fs3d.RM_VOXELS | fs3d.RM_NO_BRICKS, fs3d.RM_VOXELS):
+                img, depth = w.raymarch(width=160, height=90, mode=mode, with_depth=True, **cam)
+                assert np.array_equal(img, ref), (k, mode)
+                assert np.array_equal(depth, rdepth), (k, mode)
+        # the map follows the cells: step, edit, march again
+        w.step(7)
+        oracle.run(g, 1, 0, 7)
+        w.fill_box((8, 2, 3), (24, 7, 5), fs3d.STONE)
+        g[3:5, 2:7, 8:24] = 3
+        img = w.raymarch(width=160, height=90, mode=fs3d.RM_VOXELS | fs3d.RM_BRICKS, **CAMS[1])
+        assert np.array_equal(img, oracle.raymarch(g, width=160, height=90, mode=1, **CAMS[1]))
+
+
+def test_brick_skipping_on_slabs_and_foreign_planes(fs3d, oracle):
+    from tests.test_push_one_gpu import LocalRanks
+    nx, ny, nz = 64, 40, 30
+    g = oracle.generate(nx, ny, nz, 2, 2)          # MIXED: mostly air
+    # one world, three slabs on this device: one kernel marches all of them, each with its own brick map
+    with fs3d.VoxelWorld(nx, ny, nz, seed=4, devices=[0, 0, 0]) as w:
+        w.upload(g)
+        for cam in CAMS:
+            ref = oracle.raymarch(g, width=192, height=108, mode=1, **cam)
+            for mode in (fs3d.RM_VOXELS | fs3d.RM_BRICKS, fs3d.RM_VOXELS | fs3d.RM_NO_BRICKS):
+                assert np.array_equal(w.raymarch(width=192, height=108, mode=mode, **cam), ref)
+    # three attached slab worlds: each marches only its own planes and jumps over the others' in one move
+    r = LocalRanks(fs3d, nx, ny, nz, 3, seed=4)
+    try:
+        r.upload(g)
+        W, H = 192, 108
+        r.worlds[0].frame_export(W, H, 3)
+        for i, w in enumerate(r.worlds):
+            w.frame_attach_local(r.worlds[0], i)
+        for cam in CAMS:
+            ref = oracle.raymarch(g, width=W, height=H, mode=1, **cam)
+            for mode in (fs3d.RM_VOXELS | fs3d.RM_BRICKS, fs3d.RM_VOXELS | fs3d.RM_NO_BRICKS):
+                for w in r.worlds:
+                    w.raymarch_to_frame(mode=mode, **cam)
+                for w in r.worlds:
+                    w.sync()
+                assert np.array_equal(r.worlds[0].frame_resolve(W, H), ref)
+    finally:
+        for w in r.worlds[1:]:
+            w.close()
+        r.worlds[0].close()
+
+
+def test_adaptive_bricks_turn_on_for_air_and_off_for_dense_scenes(fs3d):
+    # the decision comes from the previous frame's steps per ray; either way the image is the same
+    n = 256
+    cam = dict(pos=(0.0, 0.0, -1.6), aspect=16.0 / 9.0, width=320, height=180)
+    for scene, expect_on in ((fs3d.SCENE_SAND_BLOCK, True), (fs3d.SCENE_RANDOM, False)):
+        with fs3d.VoxelWorld(n, n, n, seed=1) as w:
+            w.generate(scene, 1)
+            forced = w.raymarch(mode=fs3d.RM_VOXELS | fs3d.RM_NO_BRICKS, **cam)
+            assert not w.raymarch_bricks_in_use()
+            imgs = [w.raymarch(mode=fs3d.RM_VOXELS, **cam) for _ in range(3)]
+            assert all(np.array_equal(i, forced) for i in imgs)
+            assert w.raymarch_bricks_in_use() == expect_on, scene

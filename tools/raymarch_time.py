@@ -1,4 +1,5 @@
-"""ad-hoc: where a ray-marched frame's time goes on one GPU (kernel vs copies vs host)."""
+"""ad-hoc: where a ray-marched frame's time goes on one GPU (kernel vs copies vs host), with the brick occupancy map
+forced on, forced off and adaptive.   python tools/raymarch_time.py [n] [scene]"""
 import sys
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import time
@@ -19,7 +20,16 @@ def t(f, reps=5):
     return min(ts), sorted(ts)[len(ts) // 2]
 img = np.empty((H, W, 4), np.uint8)
 print("scene", scene, "n", n)
-print("fs3d_raymarch (kernel + D2H into pageable numpy), ms min/med:", t(lambda: w.raymarch(width=W, height=H, mode=fs3d.RM_VOXELS, **cam)))
 blob = w.frame_export(W, H, 1); w.frame_attach(blob, 0)
-print("raymarch_to_frame + sync (kernel only), ms:", t(lambda: (w.raymarch_to_frame(mode=fs3d.RM_VOXELS, **cam), w.sync())))
+for name, extra in (("no bricks", fs3d.RM_NO_BRICKS), ("bricks (map cached: static scene)", fs3d.RM_BRICKS), ("adaptive", 0)):
+    mode = fs3d.RM_VOXELS | extra
+    print(f"{name}: fs3d_raymarch (kernel + D2H into pageable numpy), ms min/med:", t(lambda: w.raymarch(width=W, height=H, mode=mode, **cam)),
+          "| raymarch_to_frame + sync (kernel only):", t(lambda: (w.raymarch_to_frame(mode=mode, **cam), w.sync())),
+          "| bricks in use:", w.raymarch_bricks_in_use())
+def stepped():
+    w.step(2); w.sync()
+    t0 = time.perf_counter(); w.raymarch_to_frame(mode=fs3d.RM_VOXELS | fs3d.RM_BRICKS, **cam); w.sync()
+    return (time.perf_counter() - t0) * 1e3
+stepped()
+print("bricks, map rebuilt after a step (build + march), ms:", min(stepped() for _ in range(4)))
 print("frame_resolve (min over slots + D2H), ms:", t(lambda: w.frame_resolve(W, H, img)))
