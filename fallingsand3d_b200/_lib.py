@@ -56,6 +56,9 @@ SIGNATURES = {
     "fs3d_step_index": (C.c_int, [_W, C.POINTER(C.c_uint64)]),
     "fs3d_step_timed": (C.c_int, [_W, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "fs3d_step_host": (C.c_int, [_W, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "fs3d_upload_packed": (C.c_int, [_W, C.c_void_p]),
+    "fs3d_download_packed": (C.c_int, [_W, C.c_void_p]),
+    "fs3d_step_host_packed": (C.c_int, [_W, C.c_void_p, C.c_void_p, C.c_uint32]),
     "fs3d_slab_step_host_begin": (C.c_int, [_W, C.c_void_p]),
     "fs3d_slab_step_host": (C.c_int, [_W, C.c_void_p, C.c_void_p, C.c_uint32]),
     "fs3d_histogram": (C.c_int, [_W, C.POINTER(C.c_uint64)]),

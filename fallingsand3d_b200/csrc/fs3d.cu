@@ -45,6 +45,10 @@ struct Slab {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // fs3d_step_host: copies overlap the kernels
     std::vector<cudaEvent_t> ev_chunk;               // 2 per in-flight chunk (uploaded, computed)
+    // fs3d_step_host_packed: two packed chunks in flight each way, and the events that hand them back
+    uint8_t *d_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] upload staging, [2,3] download staging
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] staging unpacked (free for the next upload), [2,3] staging downloaded
     unsigned long long *d_scratch = nullptr;   // 256 + 1 u64 + 1 u32 flag
     uint8_t *d_img = nullptr; size_t img_bytes = 0;
     float *d_palette = nullptr;
@@ -312,6 +316,8 @@ static void free_slab(Slab &s) {
     cudaEvent_t evs[] = {s.ev_edges, s.ev_done, s.ev_out_lo, s.ev_out_hi, s.ev_t0, s.ev_t1};
     for (auto e : evs) if (e) cudaEventDestroy(e);
     for (auto e : s.ev_chunk) if (e) cudaEventDestroy(e);
+    for (auto e : s.ev_stage) if (e) cudaEventDestroy(e);
+    for (auto p : s.d_stage) if (p) cudaFree(p);
     if (s.s_h2d) cudaStreamDestroy(s.s_h2d);
     if (s.s_d2h) cudaStreamDestroy(s.s_d2h);
     if (s.s_main) cudaStreamDestroy(s.s_main);
@@ -1167,6 +1173,64 @@ int fs3d_download(fs3d_world *w, uint8_t *host) {
     return sync_all(w);
 }
 
+// packed transfers (the checkpoint encoding without its header): companions of fs3d_step_host_packed
+static int transfer_packed(fs3d_world *w, uint8_t *host, bool up) {
+    int rc = sync_all(w);
+    if (rc) return rc;
+    const size_t pb = plane_bytes(w);
+    const uint32_t div = w->version == 2 ? 2u : 4u;
+    const uint32_t zbase = w->slabs[0].z0;
+    const int buf = up ? (w->cur ^ 1) : w->cur;          // uploads are staged in the back buffer and validated there
+    const uint32_t planes_per_chunk = (uint32_t)std::max<uint64_t>(1, (64ull << 20) / (pb / div));
+    bool bad = false;
+    for (auto &s : w->slabs) {
+        FS3D_CUDA(cudaSetDevice(s.device));
+        uint32_t *packed = nullptr;
+        const uint32_t cp = std::min(planes_per_chunk, s.nzl);
+        FS3D_CUDA(cudaMalloc(&packed, (size_t)cp * (pb / div)));
+        uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
+        FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
+        cudaError_t err = cudaSuccess;
+        for (uint32_t z = 0; z < s.nzl && err == cudaSuccess; z += cp) {
+            const uint32_t n = std::min(cp, s.nzl - z);
+            const uint64_t n16 = pb * n / 16, nbytes = n16 * (16 / div);
+            uint8_t *h = host + pb / div * (size_t)(s.z0 - zbase + z);
+            uint8_t *cells = owned_ptr(w, s, buf) + pb * z;
+            if (up) {
+                err = cudaMemcpyAsync(packed, h, nbytes, cudaMemcpyHostToDevice, s.s_main);
+                if (w->version == 2) unpack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint2 *>(packed), n16, cells);
+                else unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(packed, n16, cells);
+                if (w->version == 2) validate_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(cells, n16, bad_bits(w), flag);
+            } else {
+                if (w->version == 2) pack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(cells, n16, reinterpret_cast<uint2 *>(packed));
+                else pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(cells, n16, packed);
+                err = cudaMemcpyAsync(h, packed, nbytes, cudaMemcpyDeviceToHost, s.s_main);
+            }
+            if (err == cudaSuccess) err = cudaStreamSynchronize(s.s_main);      // `packed` is reused by the next chunk
+            w->launches++;
+        }
+        uint32_t f = 0;
+        if (err == cudaSuccess) err = cudaMemcpy(&f, flag, sizeof(f), cudaMemcpyDeviceToHost);
+        cudaFree(packed);
+        FS3D_CUDA(err);
+        bad = bad || f != 0;
+    }
+    if (!up) return FS3D_OK;
+    if (bad) return fail(FS3D_ERR_BAD_MATERIAL, std::string("packed upload: ") + bad_material_msg(w));
+    w->cur ^= 1;
+    return refresh_ghosts(w);
+}
+
+int fs3d_upload_packed(fs3d_world *w, const uint8_t *packed) {
+    if (!w || !packed) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    return transfer_packed(w, const_cast<uint8_t *>(packed), true);
+}
+
+int fs3d_download_packed(fs3d_world *w, uint8_t *packed) {
+    if (!w || !packed) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    return transfer_packed(w, packed, false);
+}
+
 // ---- reductions --------------------------------------------------------------------------------------
 int fs3d_histogram(fs3d_world *w, uint64_t counts[256]) {
     if (!w || !counts) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
@@ -1373,7 +1437,9 @@ int fs3d_slab_pass_steps(fs3d_world *w, uint32_t n_steps) {
 // ---- out-of-core / end-to-end step: host grid in, host grid out, copies overlapped with compute ----
 // Streams the planes a single-slab world holds through the GPU; the ghost planes of the front buffer must
 // already be right (STONE at the global boundary, the neighbours' edge planes for a rank's slab).
-static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
+// packed = the host keeps the grid in the checkpoint encoding (2 bits per voxel, 4 for schedule version 2): only those
+// bytes cross PCIe; every chunk is unpacked after its upload and packed before its download on the step stream.
+static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps, bool packed = false) {
     int rc = sync_all(w);
     if (rc) return rc;
     Slab &s = w->slabs[0];
@@ -1395,6 +1461,17 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
         FS3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         s.ev_chunk.push_back(e);
     }
+    const uint32_t div = w->version == 2 ? 2u : 4u;         // voxels per packed byte
+    if (packed) {
+        const size_t need = (size_t)pairs_per_chunk * 2 * pb / div;
+        if (s.stage_bytes < need) {
+            for (auto &p : s.d_stage) { if (p) cudaFree(p); p = nullptr; }
+            s.stage_bytes = 0;
+            for (auto &p : s.d_stage) FS3D_CUDA(cudaMalloc(&p, need));
+            s.stage_bytes = need;
+        }
+        for (auto &e : s.ev_stage) if (!e) FS3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     uint32_t *flag = reinterpret_cast<uint32_t *>(s.d_scratch + 258);
     FS3D_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), s.s_main));
     launch_skip_map(w, s);
@@ -1408,17 +1485,46 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
         uint32_t lo = L.lz_first + 2 * p0, hi = L.lz_first + 2 * p1;
         lo = std::max(lo, 1u); hi = std::min(hi, s.nzl + 1);
         const size_t off = pb * lo, bytes = pb * (size_t)(hi - lo);
-        FS3D_CUDA(cudaMemcpyAsync(src + off, host_in + pb * (size_t)(lo - 1), bytes, cudaMemcpyHostToDevice, s.s_h2d));
-        FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
-        FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
-        validate_kernel<<<grid_for(bytes / 16, s), 256, 0, s.s_main>>>(src + off, bytes / 16, bad_bits(w), flag);
-        FS3D_CUDA(cudaGetLastError());
+        const uint64_t n16 = bytes / 16;
+        if (packed) {
+            // upload the packed chunk into staging slot c & 1 (free once chunk c - 2 was unpacked), unpack it into place
+            if (c >= 2) FS3D_CUDA(cudaStreamWaitEvent(s.s_h2d, s.ev_stage[c & 1], 0));
+            FS3D_CUDA(cudaMemcpyAsync(s.d_stage[c & 1], host_in + pb / div * (size_t)(lo - 1), bytes / div, cudaMemcpyHostToDevice, s.s_h2d));
+            FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
+            FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
+            if (w->version == 2) unpack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint2 *>(s.d_stage[c & 1]), n16, src + off);
+            else unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint32_t *>(s.d_stage[c & 1]), n16, src + off);
+            FS3D_CUDA(cudaGetLastError());
+            FS3D_CUDA(cudaEventRecord(s.ev_stage[c & 1], s.s_main));
+            w->launches++;
+        } else {
+            FS3D_CUDA(cudaMemcpyAsync(src + off, host_in + pb * (size_t)(lo - 1), bytes, cudaMemcpyHostToDevice, s.s_h2d));
+            FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
+            FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
+        }
+        if (!packed || w->version == 2) {       // 2-bit codes cannot be out of range
+            validate_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(src + off, n16, bad_bits(w), flag);
+            FS3D_CUDA(cudaGetLastError());
+            w->launches++;
+        }
         rc = launch_pairs(w, s, p0, p1, ns);
         if (rc) { w->force_live = false; return rc; }
+        if (packed) {
+            // pack the stepped chunk into staging slot 2 + (c & 1) (free once chunk c - 2 was downloaded)
+            if (c >= 2) FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_stage[2 + (c & 1)], 0));
+            if (w->version == 2) pack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(dst + off, n16, reinterpret_cast<uint2 *>(s.d_stage[2 + (c & 1)]));
+            else pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(dst + off, n16, reinterpret_cast<uint32_t *>(s.d_stage[2 + (c & 1)]));
+            FS3D_CUDA(cudaGetLastError());
+            w->launches++;
+        }
         FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c + 1], s.s_main));
         FS3D_CUDA(cudaStreamWaitEvent(s.s_d2h, s.ev_chunk[2 * c + 1], 0));
-        FS3D_CUDA(cudaMemcpyAsync(host_out + pb * (size_t)(lo - 1), dst + off, bytes, cudaMemcpyDeviceToHost, s.s_d2h));
-        w->launches++;   // validate_kernel
+        if (packed) {
+            FS3D_CUDA(cudaMemcpyAsync(host_out + pb / div * (size_t)(lo - 1), s.d_stage[2 + (c & 1)], bytes / div, cudaMemcpyDeviceToHost, s.s_d2h));
+            FS3D_CUDA(cudaEventRecord(s.ev_stage[2 + (c & 1)], s.s_d2h));
+        } else {
+            FS3D_CUDA(cudaMemcpyAsync(host_out + pb * (size_t)(lo - 1), dst + off, bytes, cudaMemcpyDeviceToHost, s.s_d2h));
+        }
     }
     w->force_live = false;
     uint32_t bad = 0;
@@ -1442,6 +1548,15 @@ int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uin
         return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host needs a single-slab world that holds the whole grid "
                                           "(ranks use fs3d_slab_step_host_begin + fs3d_slab_step_host)");
     return step_host_stream(w, host_in, host_out, n_steps);
+}
+
+int fs3d_step_host_packed(fs3d_world *w, const uint8_t *packed_in, uint8_t *packed_out, uint32_t n_steps) {
+    if (!w || !packed_in || !packed_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host_packed advances 1 or 2 steps per call");
+    if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
+    if (w->slabs.size() != 1 || (w->external && w->desc.nz != w->slabs[0].nzl))
+        return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host_packed needs a single-slab world that holds the whole grid");
+    return step_host_stream(w, packed_in, packed_out, n_steps, true);
 }
 
 // One rank's share of the same end-to-end step.  _begin uploads the slab's two edge planes and stores them into the

@@ -267,7 +267,8 @@ __global__ void raymarch_kernel(const RMParams p) {
                 return true;
             };
             const int max_steps = n[0] + n[1] + n[2] + 3;
-            uint32_t cbx = 0xFFFFFFFFu, cby = 0xFFFFFFFFu, cbz = 0xFFFFFFFFu;     // brick whose occupancy bit is cached
+            uint32_t cbx = 0xFFFFFFFFu, cby = 0xFFFFFFFFu, cbz = 0xFFFFFFFFu;     // brick whose occupancy bit is cached ...
+            int csl = -1;                                                         // ... of which slab (a brick can straddle two)
             bool cached_occ = true;
             int s = 0;
             for (; s < max_steps; ++s) {
@@ -284,8 +285,8 @@ __global__ void raymarch_kernel(const RMParams p) {
                 for (int q = 0; q < p.nslabs; ++q) if ((uint32_t)gz >= p.slab_z0[q] && (uint32_t)gz < p.slab_z1[q]) sl = q;
                 if (p.bricks[sl] != nullptr) {
                     const uint32_t bx = (uint32_t)gx >> 3, by = (uint32_t)gy >> 3, bz = (uint32_t)gz >> 3;
-                    if (bx != cbx || by != cby || bz != cbz) {
-                        cbx = bx; cby = by; cbz = bz;
+                    if (bx != cbx || by != cby || bz != cbz || sl != csl) {
+                        cbx = bx; cby = by; cbz = bz; csl = sl;
                         const uint32_t nbx = p.nx >> 3, nby = (p.ny + 7u) >> 3;
                         cached_occ = (p.bricks[sl][brick_word(nbx, nby, bx, by, bz - (p.slab_z0[sl] >> 3))] >> brick_bit(bx)) & 1u;
                     }

@@ -163,6 +163,32 @@ class VoxelWorld:
                                         grid_out.ctypes.data_as(C.c_void_p), int(n)))
         return grid_out
 
+    def _packed_size(self):
+        return self.nx * self.ny * (self.z_end - self.z_begin) // (2 if self.schedule_version == 2 else 4)
+
+    def upload_packed(self, packed):
+        assert packed.dtype == np.uint8 and packed.flags.c_contiguous and packed.size == self._packed_size()
+        _check(self._lib.fs3d_upload_packed(self._h, packed.ctypes.data_as(C.c_void_p)))
+
+    def download_packed(self, out=None):
+        if out is None:
+            out = np.empty(self._packed_size(), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self._packed_size()
+        _check(self._lib.fs3d_download_packed(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def step_host_packed(self, packed_in, packed_out=None, n=1):
+        """Same for a grid the host keeps packed in the checkpoint encoding (checkpoint.pack2 / pack4): uint8 arrays of
+        nx * ny * nz / 4 bytes (/ 2 for schedule version 2)."""
+        if packed_out is None:
+            packed_out = packed_in
+        per = 2 if self.schedule_version == 2 else 4
+        for g in (packed_in, packed_out):
+            assert g.dtype == np.uint8 and g.flags.c_contiguous and g.size * per == self.nx * self.ny * (self.z_end - self.z_begin)
+        _check(self._lib.fs3d_step_host_packed(self._h, packed_in.ctypes.data_as(C.c_void_p),
+                                               packed_out.ctypes.data_as(C.c_void_p), int(n)))
+        return packed_out
+
     # ---- checkpoint (format in include/fs3d.h; numpy reader/writer in checkpoint.py) ----
     def save(self, path):
         _check(self._lib.fs3d_save(self._h, str(path).encode()))

@@ -187,6 +187,14 @@ int  fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kerne
  * (use pinned host memory).  host_in may equal host_out.  Single-slab worlds only. */
 int  fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps);
 
+/* The same for a grid the host keeps PACKED in the checkpoint encoding (the payload of fs3d_save without its header:
+ * 2 bits per voxel, 4 for FS3D_FLAG_MATERIALS8 worlds): a quarter (half) of the bytes cross PCIe — which is what bounds
+ * fs3d_step_host — and a quarter of the host memory holds the grid.  Chunks are unpacked after their upload and packed
+ * before their download on the step stream.  packed_in may equal packed_out. */
+int  fs3d_step_host_packed(fs3d_world *w, const uint8_t *packed_in, uint8_t *packed_out, uint32_t n_steps);
+int  fs3d_upload_packed(fs3d_world *w, const uint8_t *packed);      /* the planes this world holds, in that encoding */
+int  fs3d_download_packed(fs3d_world *w, uint8_t *packed);
+
 /* The same for one rank's slab of a fused-halo-push world (after fs3d_slab_ipc_attach):
  *   fs3d_slab_step_host_begin(w, host_in)   uploads the slab's two edge planes and stores them into the
  *                                           neighbours' ghost planes over peer memory

@@ -323,3 +323,35 @@ def test_gpu_settles_tie_free_scenes_like_the_sweep(fs3d, oracle):
             assert w.activity()[0] == 0, f"{name}: GPU world not settled after {t} steps"
             got = w.download()
         assert np.array_equal(got, want), f"{name}: GPU settled state differs from the sweep's / the closed form"
+
+
+@pytest.mark.parametrize("dims,m8", [((64, 40, 30), False), ((2048, 24, 20), False), ((256, 300, 9), False), ((32, 5, 1), False),
+                                     ((128, 40, 18), True), ((2048, 12, 7), True)])
+def test_step_host_packed_streams_a_packed_host_grid(fs3d, oracle, dims, m8):
+    # the host keeps the grid in the checkpoint encoding (2 or 4 bits per voxel); only those bytes cross PCIe
+    from fallingsand3d_b200 import checkpoint
+    nx, ny, nz = dims
+    version = 2 if m8 else 1
+    pack, unpack = (checkpoint.pack4, checkpoint.unpack4) if m8 else (checkpoint.pack2, checkpoint.unpack2)
+    g = oracle.generate(nx, ny, nz, 6 if m8 else 4, 6)
+    host = np.ascontiguousarray(pack(g))
+    out = np.empty_like(host)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=11, flags=fs3d.FLAG_MATERIALS8 if m8 else 0) as w:
+        t = 0
+        for n in (2, 1, 1, 2, 2, 1):
+            if n == 2 and t % 2:
+                n = 1
+            w.step_host_packed(host, out, n)
+            oracle.run(g, 11, t, n, version=version)
+            t += n
+            assert np.array_equal(unpack(out, g.size).reshape(g.shape), g), f"after step {t}"
+            assert np.array_equal(w.download(), g)
+            host, out = out, host
+        w.step_host_packed(host, host, 1)                # in place
+        oracle.run(g, 11, t, 1, version=version)
+        assert np.array_equal(unpack(host, g.size).reshape(g.shape), g)
+        assert np.array_equal(w.download_packed(), host)  # packed download / upload are the same encoding
+        w.upload_packed(np.ascontiguousarray(pack(g[::-1].copy())))
+        assert np.array_equal(w.download(), g[::-1])
+        with pytest.raises(fs3d.Fs3dError):
+            w.step_host_packed(host, out, 3)
