@@ -777,46 +777,43 @@ static __global__ void skip_plan_kernel(const PlanParams q) {   // static: step_
             }
             return __ballot_sync(0xFFFFFFFFu, act);
         };
-        // two sweeps: count this pair group's runs, reserve them with ONE atomic, then write them in y order
-        // (so neighbouring warps of the march get neighbouring segments of one pair)
-        constexpr uint32_t CACHE = 4;              // masks of the first sweep are kept for up to 128 tiles
-        uint32_t cache[CACHE];
-        uint32_t count = 0, at = 0;
-        for (int sweep = 0; sweep < 2; ++sweep) {
-            int32_t start = -1;
-            for (uint32_t base = 0, wi = 0; base <= nblk; base += 32u, ++wi) {
-                uint32_t mask;
-                if (sweep == 0) { mask = live_mask(base, true); if (wi < CACHE) cache[wi] = mask; }
-                else mask = wi < CACHE ? cache[wi] : live_mask(base, false);
-                if (lane == 0) {
-                    for (uint32_t k = 0; k < 32u && base + k <= nblk; ++k) {
-                        const uint32_t b = base + k;
-                        const bool a = (mask >> k) & 1u;           // tile b live (never for b >= nblk)
-                        if (start >= 0 && !a) {
-                            // live tiles [start, b): iterations [BLK·start, BLK·b + NS) — the tail stores the last tile's top planes
-                            const uint32_t it_a = (uint32_t)start << q.blk_log2;
-                            uint32_t it_e = (b << q.blk_log2) + q.ns;
-                            if (it_e > q.nit) it_e = q.nit;
-                            const uint32_t len = it_e - it_a;
-                            const uint32_t pcs = (len + chop_it - 1u) / chop_it;
-                            const uint32_t plen = (len + pcs - 1u) / pcs;
-                            if (sweep == 0) {
-                                count += pcs; ++my_ranges; my_iters += len;
-                            } else {
-                                for (uint32_t i = 0; i < pcs; ++i) {
-                                    const uint32_t ra = it_a + i * plen, rb = ra + plen < it_e ? ra + plen : it_e;
-                                    if (ra >= rb) break;
-                                    q.runs[3u * at] = pg; q.runs[3u * at + 1u] = ra; q.runs[3u * at + 2u] = rb;
-                                    ++at;
-                                }
-                            }
-                            start = -1;
-                        }
-                        if (a && start < 0) start = (int32_t)b;
+        // One sweep over the y-tiles, 32 at a time.  Lane 0 walks the live mask range by range (find-first-set jumps, not
+        // bit by bit); a range that is still open at the end of a word carries over.  Each finished range reserves its
+        // pieces in the run list with one atomic (the order of runs in the list is arbitrary).
+        int32_t start = -1;
+        for (uint32_t base = 0; base <= nblk; base += 32u) {
+            const uint32_t mask = live_mask(base, true);
+            if (lane != 0) continue;
+            const uint32_t nvalid = nblk + 1u - base < 32u ? nblk + 1u - base : 32u;     // tile nblk is never live: it closes a range
+            uint32_t pos = 0;
+            while (pos < nvalid) {
+                if (start < 0) {
+                    const uint32_t m = mask >> pos;
+                    if (!m) break;
+                    pos += (uint32_t)__ffs((int)m) - 1u;
+                    start = (int32_t)(base + pos);
+                } else {
+                    const uint32_t m = ~mask >> pos;                 // first tile that is not live
+                    const uint32_t skip = m ? (uint32_t)__ffs((int)m) - 1u : 32u;
+                    if (pos + skip >= 32u && base + 32u <= nblk) break;               // the range runs on into the next word
+                    pos += skip;
+                    const uint32_t bend = base + pos;                // live tiles [start, bend): iterations [BLK·start, BLK·bend + NS)
+                    const uint32_t it_a = (uint32_t)start << q.blk_log2;
+                    uint32_t it_e = (bend << q.blk_log2) + q.ns;     // the tail stores the last tile's top planes
+                    if (it_e > q.nit) it_e = q.nit;
+                    const uint32_t len = it_e - it_a;
+                    const uint32_t pcs = (len + chop_it - 1u) / chop_it;
+                    const uint32_t plen = (len + pcs - 1u) / pcs;
+                    uint32_t at = atomicAdd(q.nruns, pcs);
+                    for (uint32_t i = 0; i < pcs; ++i) {
+                        const uint32_t ra = it_a + i * plen, rb = ra + plen < it_e ? ra + plen : it_e;
+                        q.runs[3u * at] = pg; q.runs[3u * at + 1u] = ra < rb ? ra : rb; q.runs[3u * at + 2u] = rb;
+                        ++at;
                     }
+                    ++my_ranges; my_iters += len;
+                    start = -1;
                 }
             }
-            if (sweep == 0 && lane == 0 && count) at = atomicAdd(q.nruns, count);
         }
     }
     if (lane == 0 && my_ranges) { atomicAdd(&q.stats_cur[2], (unsigned long long)my_ranges); atomicAdd(&q.stats_cur[3], my_iters); }
