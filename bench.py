@@ -374,6 +374,8 @@ def ours(args):
     K, Wm = args.steps, max(args.warmup, 3)
     hbm_peak, peak_src = peaks()
     voxels = n * n * n
+    Wwarm = (Wm + 3) // 4 * 4       # warm-up steps actually run: rounded up to a multiple of four so that the timed
+                                    # steps start where a four-step pass can (and the digest is comparable across N)
 
     single = None
     if world_size == 1:
@@ -381,7 +383,7 @@ def ours(args):
         if not args.fused_only:
             w1 = fs3d.VoxelWorld(n, n, n, seed=1, flags=fs3d.FLAG_NO_FUSE)
             w1.generate(SCENE_MIXED_NOISE, 1)
-            w1.step(Wm + (Wm & 1))     # the same (even) warm-up as the fused world: digests are always comparable
+            w1.step(Wwarm)             # the same warm-up as the fused world: digests are always comparable
             w1.sync()
             ms1, l1 = w1.step_timed(K)
             d1 = w1.digest()
@@ -390,14 +392,28 @@ def ours(args):
             single = {"value": voxels * K / (ms1 * 1e-3), "ms_per_step": ms1 / K, "gpu_launches": int(l1),
                       "achieved": a1, "frac": a1 / hbm_peak, "digest": hex(d1),
                       "note": "FS3D_FLAG_NO_FUSE: one pass (1 B read + 1 B written per voxel) per step"}
-        # (b) the product path: fs3d_step fuses steps 2k, 2k+1 into one pass (1 B per voxel-update)
+        # (a2) two steps per pass (FS3D_FLAG_NO_FUSE4): the product path of every world the four-step kernel does not serve
+        two = None
+        if not args.fused_only:
+            w2 = fs3d.VoxelWorld(n, n, n, seed=1, flags=fs3d.FLAG_NO_FUSE4)
+            w2.generate(SCENE_MIXED_NOISE, 1)
+            w2.step(Wwarm)
+            w2.sync()
+            ms2, l2 = w2.step_timed(K)
+            d2 = w2.digest()
+            w2.close()
+            a2 = 2.0 * voxels * K / (ms2 * 1e-3) / 1e9
+            two = {"value": voxels * K / (ms2 * 1e-3), "ms_per_step": ms2 / K, "gpu_launches": int(l2), "achieved": a2,
+                   "frac": a2 / hbm_peak, "digest": hex(d2), "note": "FS3D_FLAG_NO_FUSE4: steps 2k, 2k+1 share a pass"}
+        # (b) the product path: fs3d_step fuses four steps into one pass where it can (rows of 1024 / 2048 voxels, single
+        # GPU: 0.5 B per voxel-update), else two
         w = fs3d.VoxelWorld(n, n, n, seed=1)
         w.generate(SCENE_MIXED_NOISE, 1)
         h0 = w.histogram()
         sampler = ClockSampler(local_rank)
         sampler.start()
         sampler.wait_ready()
-        w.step(Wm + (Wm & 1))          # keep the step index even so every timed pass is a fused pair
+        w.step(Wwarm)                  # a multiple of four: every timed pass is a whole fused pass
         w.sync()
         sampler.mark()
         ms, launches = w.step_timed(K)
@@ -406,6 +422,7 @@ def ours(args):
         digest = w.digest()
         if single is not None:
             assert single["digest"] == hex(digest), "fused and unfused runs disagree"
+            assert two["digest"] == hex(digest), "four-step and two-step passes disagree"
     else:
         sw = SlabWorld(n, n, n, seed=1)
         sw.generate(SCENE_MIXED_NOISE, 1)
@@ -414,7 +431,7 @@ def ours(args):
         if rank == 0:
             sampler.start()
             sampler.wait_ready()
-        sw.step(Wm + (Wm & 1))          # same (even) warm-up as at N = 1, so the digest is comparable across N
+        sw.step(Wwarm)                  # same warm-up as at N = 1, so the digest is comparable across N
         sw.sync()
         if sw.p2p:
             sw.engine.world.push_wait_stats()       # reset: only the timed region's halo waits are reported
@@ -455,7 +472,7 @@ def ours(args):
 
     value = voxels * K / (ms * 1e-3)
     achieved = 2.0 * voxels * K / (ms * 1e-3) / 1e9 / world_size     # per-GPU algorithmic GB/s
-    total_steps = Wm + (Wm & 1) + K
+    total_steps = Wwarm + K
     digest_check = golden_digest_check(n, total_steps, digest)
     p2p = True if world_size == 1 else bool(sw.p2p)
 
@@ -582,11 +599,14 @@ def ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_voxel_update": 2, "kernel": "fs3d::step_kernel<NS=2> (two steps per launch)",
+                     "algorithmic_bytes_per_voxel_update": 2,
+                     "kernel": ("fs3d::step4_kernel (four steps per launch)" if (world_size == 1 and n in (1024, 2048) and launches * 4 <= K + 3)
+                                else "fs3d::step_kernel<NS=2> (two steps per launch)"),
                      "note": "achieved = 2 B x voxel-updates per launch / duration, per GPU. One launch advances every "
-                             "voxel TWO steps while moving ~2 B per voxel, so frac can exceed 1: the real DRAM bytes "
+                             "voxel several steps while moving ~2 B per voxel, so frac can exceed 1: the real DRAM bytes "
                              "are `traffic`; `single_step` is the unfused kernel the 2 B/update roofline describes"},
         "single_step": single,
+        "two_steps_per_pass": two if world_size == 1 else None,
         "halo_wait": halo_wait if world_size > 1 else None,
         "extra": extra,
         "cpu_baseline": cpu,

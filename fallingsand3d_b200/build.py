@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfs3d.so")
 # tuning experiments: FS3D_NVCC_EXTRA="-DFOO=1" FS3D_LIB_OUT=/path/libfs3d_foo.so python -m fallingsand3d_b200.build --force
-SOURCES = [os.path.join(CSRC, "fs3d.cu"), os.path.join(CSRC, "fs3d_v2.cu")]
-HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "bitslice.cuh", "bitslice3.cuh", "aux_kernels.cuh", "step_kernel.cuh", "step_dispatch.cuh", "raymarch.cuh")] + [
+SOURCES = [os.path.join(CSRC, "fs3d.cu"), os.path.join(CSRC, "fs3d_v2.cu"), os.path.join(CSRC, "fs3d_s4.cu")]
+HEADERS = [os.path.join(CSRC, f) for f in ("common.cuh", "bitslice.cuh", "bitslice3.cuh", "aux_kernels.cuh", "step_kernel.cuh", "step_dispatch.cuh", "step4_kernel.cuh", "raymarch.cuh")] + [
     os.path.join(HERE, "..", "include", "fs3d.h")
 ]
 
@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
-    "--threads", "2",   # the two translation units (schedule version 1 / version 2 kernels) compile side by side
+    "--threads", "3",   # the two translation units (schedule version 1 / version 2 kernels) compile side by side
     "--fmad=false",  # raymarch parity: no silent FMA contraction anywhere in this TU (integer kernels unaffected)
 ]
 

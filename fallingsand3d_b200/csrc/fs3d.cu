@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "aux_kernels.cuh"
 #include "step_dispatch.cuh"
+#include "step4_kernel.cuh"
 #include "raymarch.cuh"
 
 namespace fs3d {
@@ -27,6 +28,9 @@ namespace fs3d {
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+cudaError_t step4_launch(int xw, const Step4Params &p, unsigned grid, cudaStream_t stream);   // fs3d_s4.cu
+uint32_t step4_units_per_cta(int xw);
 
 constexpr uint64_t SMALL_GRID_VOXELS = 1ull << 27;      // per slab; 512^3 measured the same either way
 
@@ -504,6 +508,42 @@ static int exchange_halos(fs3d_world *w) {
     return FS3D_OK;
 }
 
+// Four steps per pass (step4_kernel.cuh): single-slab worlds of schedule version 1 that hold the whole grid, without
+// skipping or halo push, rows of exactly 1024 or 2048 voxels; the step index must be a multiple of four.
+static bool fuse4_ok(const fs3d_world *w) {
+    static const bool off = std::getenv("FS3D_NO_FUSE4") != nullptr;      // A/B switch
+    if (off || (w->desc.flags & (FS3D_FLAG_NO_FUSE | FS3D_FLAG_NO_FUSE4 | FS3D_FLAG_SKIP_SETTLED))) return false;
+    if (w->version != 1 || w->slabs.size() != 1 || w->p2p) return false;
+    const Slab &s = w->slabs[0];
+    if (s.z0 != 0 || s.nzl != w->desc.nz || s.nzl < 2 || w->desc.ny < 2) return false;
+    return w->desc.nx == 1024 || w->desc.nx == 2048;
+}
+
+static int launch_fused4(fs3d_world *w, Slab &s) {
+    Step4Params p{};
+    p.src = s.buf[w->cur];
+    p.dst = s.buf[w->cur ^ 1];
+    p.nx = w->desc.nx; p.ny = w->desc.ny; p.wpr = w->desc.nx / 32;
+    p.nzl = s.nzl;
+    p.nA = (s.nzl - 1) / 2 + 1;                 // pair_layout with lz_first = 1
+    p.nB = s.nzl / 2 + 1;                       // pair_layout with lz_first = 0
+    p.nbands = (p.nB + S4_P - 1) / S4_P;
+    p.nit = w->desc.ny / 2 + 4;
+    for (int i = 0; i < 4; ++i) {
+        p.key_xy[i] = step_key(w->desc.seed, w->step + (uint64_t)i, 0);
+        p.key_zy[i] = step_key(w->desc.seed, w->step + (uint64_t)i, 1);
+    }
+    const int xw = (int)(p.wpr / 32);
+    // one CTA per SM, but never fewer than ~16 iterations per unit
+    const uint64_t total = (uint64_t)p.nbands * p.nit;
+    const uint64_t units = std::max<uint64_t>(1, total / 16);
+    const uint64_t upc = step4_units_per_cta(xw);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s.num_sms, (units + upc - 1) / upc));
+    FS3D_CUDA(step4_launch(xw, p, grid, s.s_main));
+    w->launches++;
+    return FS3D_OK;
+}
+
 // one pass over the grid = ns fused SCHEDULE.md steps (ns = 2 needs an even step index)
 static int step_pass(fs3d_world *w, int ns) {
     const int n = (int)w->slabs.size();
@@ -514,7 +554,8 @@ static int step_pass(fs3d_world *w, int ns) {
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
         static const bool force_push = std::getenv("FS3D_DEBUG_FORCE_PUSH") != nullptr;   // timing experiments only
-        if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
+        if (!rc && ns == 4) rc = launch_fused4(w, s);
+        else if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
         if (rc) return rc;
         // every warp of an edge pair adds the iterations it finished: nit of this pass x warps per pair
         if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
@@ -998,7 +1039,9 @@ int fs3d_step(fs3d_world *w, uint32_t n_steps) {
     uint32_t left = n_steps;
     while (left > 0) {
         // steps 2k and 2k + 1 share the z-pairing and x-offset, so they fuse into one pass
-        const int ns = (left >= 2 && (w->step & 1) == 0 && !(w->desc.flags & FS3D_FLAG_NO_FUSE)) ? 2 : 1;
+        // and four steps starting on a multiple of four share one pass where step4_kernel.cuh applies
+        const int ns = (left >= 4 && (w->step & 3) == 0 && fuse4_ok(w)) ? 4
+                     : (left >= 2 && (w->step & 1) == 0 && !(w->desc.flags & FS3D_FLAG_NO_FUSE)) ? 2 : 1;
         int rc = step_pass(w, ns);
         if (rc) return rc;
         left -= (uint32_t)ns;

@@ -1,0 +1,250 @@
+// step4_kernel.cuh — FOUR SCHEDULE.md steps per pass (0.5 B of DRAM traffic per voxel-update), schedule version 1.
+//
+// Steps t .. t+3 with t ≡ 0 (mod 4): steps t, t+1 use hoff = 0 ("stage A": x-offset 0, ZY pairs (0,1), (2,3), …), steps
+// t+2, t+3 use hoff = 1 ("stage B": x-offset 1, ZY pairs (−1,0), (1,2), …).  Inside a stage a z-pair of rows is closed
+// under both steps (that is the two-step pass of step_kernel.cuh); between the stages the pairing shifts by one row, so
+// stage B's pair q = (plane 2q, 2q+1) takes the upper row of stage-A pair q−1 and the lower row of stage-A pair q.
+//
+// A warp stays autonomous (no barrier, no other warp's data): it owns a BAND of P consecutive B-pairs and walks the grid
+// in y-blocks of K iterations; inside a y-block it visits the band's P+1 A-pairs one after the other —
+//     load pair a  →  stage A (two steps)  →  its upper row's finished planes go into a K-deep shared-memory buffer,
+//     stage B (two more steps) on (the previous pair's upper row out of that buffer, this pair's lower row)  →  store
+// — and parks each pair's pipeline state (the carried planes of both stages: 28 words per lane) in shared memory until
+// the next y-block.  The first A-pair of a band is recomputed by the band below ((P+1)/P of the loads and of stage A);
+// everything else is done once.  DRAM sees every byte read (P+1)/P times and written once per FOUR steps.
+// Rows of 2048 voxels use two warps per band (XW = 2), which exchange the word-boundary cells of stage B's odd
+// x-offset through the tagged mailboxes of step_kernel.cuh.
+//
+// Used by fs3d_step for single-slab worlds (no halo push, no skipping) with nx = 1024 or 2048 when four steps remain and
+// the step index is a multiple of four; everything else keeps the two-step pass.  Results are identical by construction
+// and tested against the oracle (every parity test with nx in {1024, 2048}, the full 2048^3 compare, bench digests).
+// No reference counterpart; call site: /root/reference/src/engine/engine.cpp:59-70.
+#pragma once
+#include "step_kernel.cuh"
+
+namespace fs3d {
+
+constexpr int S4_P = 6;            // B-pairs per band
+constexpr int S4_K = 8;            // iterations per y-block
+constexpr uint32_t S4_LEAD = 7;    // warm-up iterations that rebuild both stages' carried planes
+constexpr uint32_t S4_WORDS_PER_LANE = (S4_P + 1) * 12 + S4_P * 16 + S4_K * 4;     // A states, B states, hand-off buffer
+
+struct Step4Params {
+    const uint8_t *src;
+    uint8_t *dst;
+    uint32_t nx, ny, wpr;
+    uint32_t nzl;                  // owned planes; the slab is the whole grid (z0 = 0), local plane 0 / nzl+1 are STONE ghosts
+    uint32_t nA, nB;               // stage-A pairs a: local planes (1+2a, 2+2a); stage-B pairs q: local planes (2q, 2q+1)
+    uint32_t nbands;               // ceil(nB / S4_P)
+    uint32_t nit;                  // march iterations: ny / 2 + 4
+    uint32_t key_xy[4], key_zy[4]; // SCHEDULE.md §3 keys of steps t .. t+3
+};
+
+template <int XW, int THREADS>
+constexpr uint32_t step4_smem_bytes() { return (THREADS / 32) * S4_WORDS_PER_LANE * 32u * 4u; }
+
+template <int XW, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) {
+    using R = Rules1;
+    using Cell = P2;
+    static_assert(XW == 1 || XW == 2, "one warp per 1024 voxels of a row");
+    constexpr bool XCH = XW == 2;
+    constexpr uint32_t UNITS = THREADS / 32 / XW;           // bands marched side by side in a CTA
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wic = threadIdx.x >> 5;
+    const uint32_t pic = wic / XW, half = wic % XW;
+    const uint32_t gw = blockIdx.x * UNITS + pic, nw = gridDim.x * UNITS;
+    __shared__ uint32_t xch_smem[XCH ? UNITS * 4 : 1];
+    volatile uint32_t *const xch = xch_smem + (XCH ? pic * 4 : 0);
+    uint32_t xseq = 0;
+    if (XCH) {
+        if (threadIdx.x < UNITS * 4) xch_smem[threadIdx.x] = 0u;
+        __syncthreads();
+    }
+    extern __shared__ __align__(16) uint32_t s4_smem[];
+    uint32_t *const sm = s4_smem + (size_t)wic * S4_WORDS_PER_LANE * 32u + lane;     // word w of this lane: sm[w * 32]
+    auto sA = [&](int k, int w) -> uint32_t & { return sm[(k * 12 + w) * 32]; };
+    auto sB = [&](int k, int w) -> uint32_t & { return sm[((S4_P + 1) * 12 + (k - 1) * 16 + w) * 32]; };
+    auto sH = [&](int slot, int w) -> uint32_t & { return sm[((S4_P + 1) * 12 + S4_P * 16 + slot * 4 + w) * 32]; };
+
+    const uint32_t xw = lane + half * 32u;                 // this lane's 32-voxel word of the row
+    const bool hasp = xw > 0u, hasn = xw + 1u < p.wpr;
+    const size_t row_bytes = p.nx, plane_bytes = (size_t)p.nx * p.ny;
+    const uint32_t ylast = p.ny - 1u;
+    const uint64_t total = (uint64_t)p.nbands * p.nit;
+    uint64_t pos = total * gw / nw;
+    const uint64_t end = total * (gw + 1) / nw;
+
+    // one-way message between the two warps of a unit (see step_kernel.cuh)
+    auto xmail = [&](uint32_t from_half, uint32_t from_lane, uint32_t payload) -> uint32_t {
+        ++xseq;
+        const uint32_t tag = (xseq & 0x3FFFu) << 18;
+        volatile uint32_t *slot = xch + (xseq & 1u);
+        if (half == from_half) {
+            if (lane == from_lane) *slot = tag | payload;
+            return 0u;
+        }
+        uint32_t v;
+        do { v = *slot; } while ((v & 0xFFFC0000u) != tag);
+        return v & 0x3FFFFu;
+    };
+    // XY sub-step on (upper, lower) of both rows; x-offset 0 (stage A) or 1 (stage B, cells of the word-straddling block
+    // cross lanes by shuffle and the warp pair's boundary through the mailbox)
+    auto xy0 = [&](Cell (&up)[2], Cell (&lw)[2], uint32_t yu, uint32_t key, const uint32_t (&hxy)[2]) {
+        R::xy0(up[0], lw[0], up[1], lw[1], hash_word(key + hxy[0] + yu * HC2), hash_word(key + hxy[1] + yu * HC2));
+    };
+    auto xy1 = [&](Cell (&up)[2], Cell (&lw)[2], uint32_t yu, uint32_t key, const uint32_t (&hxy)[2]) {
+        const uint32_t r0 = hash_word(key + hxy[0] + yu * HC2), r1 = hash_word(key + hxy[1] + yu * HC2);
+        const uint32_t first = R::first_bits(up[0], lw[0], up[1], lw[1]);
+        uint32_t xin = R::NB_STONE;
+        if (XCH) xin = xmail(1u, 0u, first);
+        uint32_t b = __shfl_down_sync(ONES, first, 1);
+        if (XCH && half == 0u && lane == 31u) b = xin;
+        uint32_t carry;
+        R::xy1(up[0], lw[0], up[1], lw[1], r0, r1, hasn ? b : R::NB_STONE, carry);
+        if (XCH) xin = xmail(0u, 31u, carry);
+        uint32_t a = __shfl_up_sync(ONES, carry, 1);
+        if (XCH && half == 1u && lane == 0u) a = xin;
+        uint32_t enw = 0;
+        const uint32_t wall = R::wall_first(first, enw);
+        if (!hasp) a = wall;
+        R::post1(up[0], lw[0], up[1], lw[1], a);
+    };
+    auto zy = [&](Cell (&up)[2], Cell (&lw)[2], uint32_t yu, uint32_t key, uint32_t hzy) {
+        R::zy(up[0], up[1], lw[0], lw[1], hash_word(key + hzy + yu * HC2));
+    };
+
+    while (pos < end) {
+        const uint32_t band = (uint32_t)(pos / p.nit);
+        const uint32_t it_a = (uint32_t)(pos - (uint64_t)band * p.nit);
+        const uint64_t left = end - pos;
+        const uint32_t it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
+        pos += it_b - it_a;
+
+        const int qa = (int)(band * S4_P);
+        const int nq = min(S4_P, (int)p.nB - qa);                 // B-pairs of this band; its A-pairs are a = qa-1 .. qa-1+nq
+        const uint32_t warm = it_a < S4_LEAD ? it_a : S4_LEAD;
+        const uint32_t it0 = it_a - warm;
+        // fresh pipelines: STONE below the segment's first plane (exact at the floor, rebuilt by the warm-up elsewhere)
+        for (int k = 0; k <= nq; ++k)
+            for (int w = 0; w < 12; ++w) sA(k, w) = ONES;
+        for (int k = 1; k <= nq; ++k)
+            for (int w = 0; w < 16; ++w) sB(k, w) = ONES;
+
+        // plane pair `itt` of A-pair kk of this band: four unconditional 256-bit loads (clamped addresses; what lies
+        // outside the grid is replaced by STONE when the words are packed)
+        Raw<1> raw;
+        auto issue = [&](int kk, uint32_t itt) {
+            const int a = qa - 1 + kk;
+            const bool ok = a >= 0 && a < (int)p.nA;
+            const uint8_t *base = p.src + (ok ? (size_t)(1 + 2 * a) * plane_bytes + (size_t)xw * 32u : (size_t)0);
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t y = 2u * itt + h;
+                    ld256(base + (size_t)r * plane_bytes + (size_t)(y < ylast ? y : ylast) * row_bytes, raw.w[0][r][h]);
+                }
+        };
+        issue(0, it0);
+
+        for (uint32_t ib = it0; ib < it_b; ib += S4_K) {
+            const uint32_t ie = ib + S4_K < it_b ? ib + S4_K : it_b;
+            for (int k = 0; k <= nq; ++k) {
+                const int a = qa - 1 + k, q = qa + k - 1;          // stage-A pair loaded now; stage-B pair finished now (k >= 1)
+                const bool a_ok = a >= 0 && a < (int)p.nA;
+                const uint32_t hxyA[2] = {xw * HC1 + (uint32_t)(2 * a) * HC3, xw * HC1 + (uint32_t)(2 * a + 1) * HC3};
+                const uint32_t hzyA = hxyA[0];
+                const uint32_t hxyB[2] = {xw * HC1 + (uint32_t)(2 * q - 1) * HC3, xw * HC1 + (uint32_t)(2 * q) * HC3};
+                const uint32_t hzyB = hxyB[0];
+                const bool own[2] = {k >= 1 && 2 * q >= 1 && 2 * q <= (int)p.nzl, k >= 1 && 2 * q + 1 <= (int)p.nzl};
+                uint8_t *const drow0 = p.dst + (size_t)(k >= 1 ? 2 * q : 0) * plane_bytes + (size_t)xw * 32u;
+
+                Cell prev1[2], c2[2], c3[2];                       // stage A's carried planes (rows r0, r1 of pair a)
+                Cell prev1B[2], c2B[2], c3B[2], bprev[2];          // stage B's (rows: pair a-1's r1, pair a's r0) + the even plane in waiting
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    prev1[r] = {sA(k, 6 * r + 0), sA(k, 6 * r + 1)}; c2[r] = {sA(k, 6 * r + 2), sA(k, 6 * r + 3)}; c3[r] = {sA(k, 6 * r + 4), sA(k, 6 * r + 5)};
+                }
+                if (k >= 1) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        prev1B[r] = {sB(k, 8 * r + 0), sB(k, 8 * r + 1)}; c2B[r] = {sB(k, 8 * r + 2), sB(k, 8 * r + 3)};
+                        c3B[r] = {sB(k, 8 * r + 4), sB(k, 8 * r + 5)}; bprev[r] = {sB(k, 8 * r + 6), sB(k, 8 * r + 7)};
+                    }
+                }
+
+                for (uint32_t it = ib; it < ie; ++it) {
+                    const uint32_t y1 = 2u * it;
+                    Cell lo[2], hi[2];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        lo[r] = R::pack(raw.w[0][r][0]);
+                        hi[r] = R::pack(raw.w[0][r][1]);
+                        if (!(a_ok && y1 < p.ny))      lo[r] = R::stone();
+                        if (!(a_ok && y1 + 1u < p.ny)) hi[r] = R::stone();
+                    }
+                    // the next plane pair's loads are in flight while this one is evaluated: next iteration of this pair,
+                    // else the next pair's first, else the next y-block's first pair
+                    if (it + 1u < ie) issue(k, it + 1u);
+                    else if (k < nq) issue(k + 1, ib);
+                    else if (ie < it_b) issue(0, ie);
+
+                    // ---- stage A: steps t (XY then ZY) and t+1 (ZY then XY), x-offset 0
+                    xy0(hi, lo, y1 + 1u, p.key_xy[0], hxyA);
+                    zy(lo, prev1, y1, p.key_zy[0], hzyA);
+                    zy(prev1, c2, y1 - 1u, p.key_zy[1], hzyA);
+                    xy0(c2, c3, y1 - 2u, p.key_xy[1], hxyA);
+                    // planes y1-3 (c3) and y1-2 (c2) are final after step t+1.  Hand this pair's upper row to the next pair
+                    // through the buffer, after taking the previous pair's upper row out of the same slot.
+                    const uint32_t slot = it - ib;
+                    Cell L3 = {sH(slot, 0), sH(slot, 1)}, L2 = {sH(slot, 2), sH(slot, 3)};
+                    sH(slot, 0) = c3[1].p0; sH(slot, 1) = c3[1].p1; sH(slot, 2) = c2[1].p0; sH(slot, 3) = c2[1].p1;
+
+                    if (k >= 1) {
+                        // ---- stage B: steps t+2 (XY then ZY) and t+3 (ZY then XY), x-offset 1, on rows (pair a-1's r1, pair a's r0)
+                        // its plane pair is (y1-4, y1-3): the even plane waited one iteration in `bprev`
+                        Cell loB[2] = {bprev[0], bprev[1]}, hiB[2] = {L3, c3[0]};
+                        const uint32_t yb1 = y1 - 4u;
+                        xy1(hiB, loB, yb1 + 1u, p.key_xy[2], hxyB);
+                        zy(loB, prev1B, yb1, p.key_zy[2], hzyB);
+                        zy(prev1B, c2B, yb1 - 1u, p.key_zy[3], hzyB);
+                        xy1(c2B, c3B, yb1 - 2u, p.key_xy[3], hxyB);
+                        if (it >= it_a) {
+                            // planes y1-7 (c3B) and y1-6 (c2B) are final after step t+3
+                            const uint32_t ya = yb1 - 3u, yb = yb1 - 2u;          // wrap to huge when negative
+#pragma unroll
+                            for (int r = 0; r < 2; ++r) {
+                                if (!own[r]) continue;
+                                uint32_t o[8];
+                                uint8_t *d = drow0 + (size_t)r * plane_bytes;
+                                if (ya < p.ny) { R::unpack(c3B[r], o); st256(d + (size_t)ya * row_bytes, o); }
+                                if (yb < p.ny) { R::unpack(c2B[r], o); st256(d + (size_t)yb * row_bytes, o); }
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) { c3B[r] = prev1B[r]; c2B[r] = loB[r]; prev1B[r] = hiB[r]; }
+                        bprev[0] = L2; bprev[1] = c2[0];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) { c3[r] = prev1[r]; c2[r] = lo[r]; prev1[r] = hi[r]; }
+                }
+
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    sA(k, 6 * r + 0) = prev1[r].p0; sA(k, 6 * r + 1) = prev1[r].p1; sA(k, 6 * r + 2) = c2[r].p0; sA(k, 6 * r + 3) = c2[r].p1;
+                    sA(k, 6 * r + 4) = c3[r].p0; sA(k, 6 * r + 5) = c3[r].p1;
+                }
+                if (k >= 1) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        sB(k, 8 * r + 0) = prev1B[r].p0; sB(k, 8 * r + 1) = prev1B[r].p1; sB(k, 8 * r + 2) = c2B[r].p0; sB(k, 8 * r + 3) = c2B[r].p1;
+                        sB(k, 8 * r + 4) = c3B[r].p0; sB(k, 8 * r + 5) = c3B[r].p1; sB(k, 8 * r + 6) = bprev[r].p0; sB(k, 8 * r + 7) = bprev[r].p1;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace fs3d

@@ -23,6 +23,7 @@ FLAG_NO_PEER_PUSH = 4
 FLAG_PEER_PUSH_SHARED_DEVICE = 8
 FLAG_EXPORTABLE = 16
 FLAG_MATERIALS8 = 32
+FLAG_NO_FUSE4 = 64
 RM_SDF_SPHERE, RM_VOXELS, RM_SRGB = 0, 1, 16
 RM_BRICKS, RM_NO_BRICKS = 32, 64      # force / forbid the 8^3-brick empty-space skipping (default: adaptive; same image)
 

@@ -76,6 +76,9 @@ extern "C" {
                                         of kernels, so worlds that hold only codes 0-3 pay nothing for it.  A version-2
                                         world that holds only codes 0-3 evolves exactly like a version-1 world. */
 
+#define FS3D_FLAG_NO_FUSE4      64u  /* never fuse FOUR steps into one pass (default: single-GPU worlds with rows of 1024 or
+                                        2048 voxels do, when four steps remain and the step index is a multiple of four) */
+
 /* scene ids for fs3d_generate (SCHEDULE.md §5) */
 #define FS3D_SCENE_EMPTY        0
 #define FS3D_SCENE_SAND_BLOCK   1

@@ -15,10 +15,15 @@ from oracle import oracle  # noqa: E402
 N = 2048
 LAST = int(sys.argv[1]) if len(sys.argv) > 1 else 106
 # steps bench.py can end on: warm-up rounded up to even (4 or 6 for --warmup 3..6) + K for K = 20, 50, 100, and a few early ones
-KEEP = sorted(set([1, 2, 3, 4, 6, 8, 13, 24, 26, 54, 56, 104, 106]))
+# (warm-up rounded up to a multiple of four — so that every timed pass of a single-GPU run is a four-step pass — + K)
+KEEP = sorted(set([1, 2, 3, 4, 6, 8, 13, 24, 26, 28, 54, 56, 58, 104, 106, 108]))
 out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench_digests.json")
 
 g = oracle.generate(N, N, N, 4, 1)
+old = {}
+if os.path.exists(out_path):                      # keep what an earlier (longer) run already established
+    with open(out_path) as f:
+        old = json.load(f).get("digests", {})
 out = {"schedule_version": oracle.lib().fs3d_oracle_schedule_version(), "dims": [N, N, N], "scene": 4, "scene_seed": 1,
        "seed": 1, "digest0": hex(oracle.digest(g)), "histogram": [int(v) for v in oracle.histogram(g)[:4]], "digests": {}}
 # a thin slab's step-0 digest, cheap to regenerate: lets the CPU test suite pin the scene the big run started from
@@ -28,6 +33,9 @@ for t in range(LAST):
     oracle.step(g, 1, t)
     if t + 1 in KEEP:
         out["digests"][str(t + 1)] = hex(oracle.digest(g))
+        assert old.get(str(t + 1), out["digests"][str(t + 1)]) == out["digests"][str(t + 1)], "oracle digest changed"
+        for k, v in old.items():
+            out["digests"].setdefault(k, v)
         with open(out_path, "w") as f:
             json.dump(out, f, indent=1)
         print(f"step {t + 1}: {out['digests'][str(t + 1)]}  ({time.time() - t0:.0f} s)", flush=True)

@@ -355,3 +355,37 @@ def test_step_host_packed_streams_a_packed_host_grid(fs3d, oracle, dims, m8):
         assert np.array_equal(w.download(), g[::-1])
         with pytest.raises(fs3d.Fs3dError):
             w.step_host_packed(host, out, 3)
+
+
+# ---- four steps per pass (step4_kernel.cuh): rows of 1024 / 2048 voxels, step index a multiple of four ----
+@pytest.mark.parametrize("dims", [(1024, 6, 5), (2048, 6, 4), (1024, 1, 2), (2048, 2, 2), (1024, 9, 3), (2048, 40, 31), (1024, 70, 26),
+                                  (2048, 33, 12), (1024, 300, 4)])
+@pytest.mark.parametrize("every", [4, 8, 5, 13])
+def test_four_step_passes_match_oracle(fs3d, oracle, dims, every):
+    # every = 4, 8: nothing but four-step passes; 5, 13: four-step passes mixed with two-step and single passes
+    nx, ny, nz = dims
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=4 if ny > 8 else 3, seed=7, steps=2 * every + 8, every=every)
+
+
+def test_four_step_passes_with_many_bands_and_segments(fs3d, oracle):
+    # more bands than units and marches cut into segments with warm-up; 13 z-planes: odd count, partial last band
+    run_and_compare(fs3d, oracle, 2048, 160, 50, scene=4, seed=3, steps=16, every=8)
+    run_and_compare(fs3d, oracle, 1024, 520, 13, scene=3, seed=5, steps=12, every=12)
+
+
+def test_four_two_and_one_step_passes_agree(fs3d):
+    for n in (1024, 2048):
+        digs = {}
+        for name, flags in (("four", 0), ("two", fs3d.FLAG_NO_FUSE4), ("one", fs3d.FLAG_NO_FUSE)):
+            with fs3d.VoxelWorld(n, 256, 64, seed=5, flags=flags) as w:
+                w.generate(fs3d.SCENE_MIXED_NOISE, 2)
+                h0 = w.histogram()
+                out = []
+                for k in (4, 8, 3, 1, 12, 40):
+                    ms, launches = w.step_timed(k)
+                    out.append((w.digest(), launches))
+                assert np.array_equal(w.histogram(), h0)
+                digs[name] = out
+        assert [d for d, _ in digs["four"]] == [d for d, _ in digs["two"]] == [d for d, _ in digs["one"]]
+        # the first call of each world starts at step 0: 4 steps = 1, 2, 4 launches
+        assert [digs[k][0][1] for k in ("four", "two", "one")] == [1, 2, 4]
