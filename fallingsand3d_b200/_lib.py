@@ -80,6 +80,8 @@ SIGNATURES = {
     "fs3d_slab_ipc_attach": (C.c_int, [_W, C.c_void_p, C.c_void_p]),
     "fs3d_slab_attach_local": (C.c_int, [_W, _W, _W]),
     "fs3d_slab_push_halos": (C.c_int, [_W]),
+    "fs3d_slab_can_fuse4": (C.c_int, [_W]),
+    "fs3d_slab_allow_fuse4": (C.c_int, [_W, C.c_int]),
     "fs3d_push_wait_stats": (C.c_int, [_W, C.POINTER(C.c_uint64)]),
     "fs3d_frame_export": (C.c_int, [_W, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64]),
     "fs3d_frame_attach": (C.c_int, [_W, C.c_void_p, C.c_uint32]),

@@ -29,7 +29,8 @@ static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-cudaError_t step4_launch(int xw, const Step4Params &p, unsigned grid, cudaStream_t stream);   // fs3d_s4.cu
+cudaError_t step4_launch(int xw, int nbr, const Step4Params &p, unsigned grid, cudaStream_t stream);   // fs3d_s4.cu
+cudaError_t halo4_launch(const Halo4Params &h, cudaStream_t stream);
 uint32_t step4_units_per_cta(int xw);
 
 constexpr uint64_t SMALL_GRID_VOXELS = 1ull << 27;      // per slab; 512^3 measured the same either way
@@ -113,6 +114,8 @@ struct fs3d_world {
     int version = 1;             // schedule version: 1 (four materials) or 2 (FS3D_FLAG_MATERIALS8: eight, SCHEDULE.md §7)
     uint8_t max_material = FS3D_STONE;
     uint64_t content_epoch = 0;  // bumps whenever cells may have changed (steps, edits): the ray-marcher's brick maps follow it
+    bool far_valid = false;      // multi-slab p2p worlds: the far ghost planes of the front buffer are current (four-step passes)
+    bool fuse4_allowed = false;  // slab worlds of several processes: every rank agreed that its slab supports four-step passes
     bool force_live = false;     // fs3d_step_host in flight: settled-tile plans treat every tile as live
     bool failed = false;         // the watchdog fired: cells are undefined, stepping is refused
 };
@@ -240,7 +243,9 @@ static void vmm_free(Slab &s, int b) {
 static int init_slab(fs3d_world *w, Slab &s) {
     FS3D_CUDA(cudaSetDevice(s.device));
     const size_t pb = plane_bytes(w);
-    s.bytes = pb * ((size_t)s.nzl + 2);
+    // planes: 0 near ghost-low, 1 .. nzl owned, nzl+1 near ghost-high, then the FAR ghosts of the four-step pass
+    // (step4_kernel.cuh): nzl+2 = global plane z1+1, nzl+3 = global plane z0-2
+    s.bytes = pb * ((size_t)s.nzl + 4);
     for (int b = 0; b < 2; ++b) {
         if (w->desc.flags & FS3D_FLAG_EXPORTABLE) { int rc = vmm_alloc(w, s, b); if (rc) return rc; }
         else FS3D_CUDA(cudaMalloc(&s.buf[b], s.bytes));
@@ -288,7 +293,7 @@ static int init_slab(fs3d_world *w, Slab &s) {
     for (int b = 0; b < 2; ++b) {
         FS3D_CUDA(cudaMemsetAsync(s.buf[b], 0, s.bytes, s.s_main));
         FS3D_CUDA(cudaMemsetAsync(s.buf[b], FS3D_STONE, pb, s.s_main));
-        FS3D_CUDA(cudaMemsetAsync(s.buf[b] + pb * ((size_t)s.nzl + 1), FS3D_STONE, pb, s.s_main));
+        FS3D_CUDA(cudaMemsetAsync(s.buf[b] + pb * ((size_t)s.nzl + 1), FS3D_STONE, 3 * pb, s.s_main));
     }
     FS3D_CUDA(cudaStreamSynchronize(s.s_main));
     return FS3D_OK;
@@ -470,6 +475,8 @@ static int launch_skip_map(fs3d_world *, Slab &s) {
 // every tile counts as active "just now", so the next four steps run everywhere
 static int touch_all_tiles(fs3d_world *w) {
     w->content_epoch++;
+    if (!w->external) w->far_valid = false;      // in-process worlds: an edit may have touched a far-ghost source plane
+                                                 // (ranks of a multi-process world reset it together in fs3d_slab_push_halos)
     for (auto &s : w->slabs) {
         if (!s.d_last_active) continue;
         FS3D_CUDA(cudaSetDevice(s.device));
@@ -508,15 +515,40 @@ static int exchange_halos(fs3d_world *w) {
     return FS3D_OK;
 }
 
-// Four steps per pass (step4_kernel.cuh): single-slab worlds of schedule version 1 that hold the whole grid, without
-// skipping or halo push, rows of exactly 1024 or 2048 voxels; the step index must be a multiple of four.
+// Four steps per pass (step4_kernel.cuh): worlds of schedule version 1 without skipping, rows of exactly 1024 or 2048
+// voxels; the step index must be a multiple of four.  Single slabs, or z-slabs wired for the fused halo push whose
+// internal boundaries lie on even planes (stage A then needs no halo at all) with at least four planes each.
+static bool slab_fuse4_capable(const fs3d_world *w, const Slab &s) {
+    if (w->version != 1 || (w->desc.flags & (FS3D_FLAG_NO_FUSE | FS3D_FLAG_NO_FUSE4 | FS3D_FLAG_SKIP_SETTLED))) return false;
+    if (w->desc.nx != 1024 && w->desc.nx != 2048) return false;
+    if (s.nzl < 2 || w->desc.ny < 2) return false;
+    const bool has_lo = s.z0 > 0, has_hi = s.z0 + s.nzl < w->desc.nz;
+    if ((has_lo || has_hi) && ((s.z0 & 1u) || s.nzl < 4)) return false;
+    if (has_hi && (s.nzl & 1u)) return false;
+    return true;
+}
 static bool fuse4_ok(const fs3d_world *w) {
     static const bool off = std::getenv("FS3D_NO_FUSE4") != nullptr;      // A/B switch
-    if (off || (w->desc.flags & (FS3D_FLAG_NO_FUSE | FS3D_FLAG_NO_FUSE4 | FS3D_FLAG_SKIP_SETTLED))) return false;
-    if (w->version != 1 || w->slabs.size() != 1 || w->p2p) return false;
-    const Slab &s = w->slabs[0];
-    if (s.z0 != 0 || s.nzl != w->desc.nz || s.nzl < 2 || w->desc.ny < 2) return false;
-    return w->desc.nx == 1024 || w->desc.nx == 2048;
+    if (off) return false;
+    for (auto &s : w->slabs) if (!slab_fuse4_capable(w, s)) return false;
+    if (w->slabs.size() == 1 && w->slabs[0].nzl == w->desc.nz) return !w->p2p;    // the whole grid in one slab
+    if (!w->p2p) return false;                          // copy / NCCL halo paths keep the two-step pass
+    return w->external ? w->fuse4_allowed : true;       // ranks decide together (fs3d_slab_allow_fuse4)
+}
+
+// deliver slab s's edge rows of buffer `b` into the neighbours' ghost planes of their buffer `b` (near = 0: far planes only)
+static int launch_halo4(fs3d_world *w, Slab &s, int b, int near) {
+    if (!s.peer_lo.valid && !s.peer_hi.valid) return FS3D_OK;
+    Halo4Params h{};
+    h.src = s.buf[b];
+    h.nzl = s.nzl;
+    h.plane_bytes = plane_bytes(w);
+    h.near = near;
+    if (s.peer_lo.valid) { h.lo_buf = s.peer_lo.buf[b]; h.lo_nzl = s.peer_lo.nzl; h.lo_flag = s.peer_lo.flags + 1; }
+    if (s.peer_hi.valid) { h.hi_buf = s.peer_hi.buf[b]; h.hi_nzl = s.peer_hi.nzl; h.hi_flag = s.peer_hi.flags + 0; }
+    FS3D_CUDA(halo4_launch(h, s.s_main));
+    w->launches++;
+    return FS3D_OK;
 }
 
 static int launch_fused4(fs3d_world *w, Slab &s) {
@@ -524,8 +556,8 @@ static int launch_fused4(fs3d_world *w, Slab &s) {
     p.src = s.buf[w->cur];
     p.dst = s.buf[w->cur ^ 1];
     p.nx = w->desc.nx; p.ny = w->desc.ny; p.wpr = w->desc.nx / 32;
-    p.nzl = s.nzl;
-    p.nA = (s.nzl - 1) / 2 + 1;                 // pair_layout with lz_first = 1
+    p.z0 = s.z0; p.nzl = s.nzl;
+    p.nA = (s.nzl - 1) / 2 + 1;                 // pair_layout with lz_first = 1 (z0 is even)
     p.nB = s.nzl / 2 + 1;                       // pair_layout with lz_first = 0
     p.nbands = (p.nB + S4_P - 1) / S4_P;
     p.nit = w->desc.ny / 2 + 4;
@@ -533,14 +565,32 @@ static int launch_fused4(fs3d_world *w, Slab &s) {
         p.key_xy[i] = step_key(w->desc.seed, w->step + (uint64_t)i, 0);
         p.key_zy[i] = step_key(w->desc.seed, w->step + (uint64_t)i, 1);
     }
+    p.has_lo = s.peer_lo.valid ? 1 : 0;
+    p.has_hi = s.peer_hi.valid ? 1 : 0;
+    p.my_flags = s.d_flags; p.wait_target = w->wait_target;
+    p.push_err = s.d_flags + 2; p.push_timeout_ns = w->push_timeout_ns;
     const int xw = (int)(p.wpr / 32);
     // one CTA per SM, but never fewer than ~16 iterations per unit
     const uint64_t total = (uint64_t)p.nbands * p.nit;
     const uint64_t units = std::max<uint64_t>(1, total / 16);
     const uint64_t upc = step4_units_per_cta(xw);
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s.num_sms, (units + upc - 1) / upc));
-    FS3D_CUDA(step4_launch(xw, p, grid, s.s_main));
+    FS3D_CUDA(step4_launch(xw, (p.has_lo || p.has_hi) ? 1 : 0, p, grid, s.s_main));
     w->launches++;
+    return FS3D_OK;
+}
+
+// a four-step pass of a p2p world: (far-ghost refresh if two-step passes ran since the last delivery) -> step4 on every
+// slab -> delivery of the new edge rows into the neighbours' ghost planes of the new front buffer
+static int fused4_pass_p2p(fs3d_world *w) {
+    if (!w->far_valid) {
+        for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); int rc = launch_halo4(w, s, w->cur, 0); if (rc) return rc; }
+        w->wait_target += HALO4_BLOCKS;
+    }
+    for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); int rc = launch_fused4(w, s); if (rc) return rc; }
+    for (auto &s : w->slabs) { FS3D_CUDA(cudaSetDevice(s.device)); int rc = launch_halo4(w, s, w->cur ^ 1, 1); if (rc) return rc; }
+    w->wait_target += HALO4_BLOCKS;
+    w->far_valid = true;
     return FS3D_OK;
 }
 
@@ -554,22 +604,28 @@ static int step_pass(fs3d_world *w, int ns) {
         PairLayout L = pair_layout(s, hoff);
         int rc = launch_skip_map(w, s);
         static const bool force_push = std::getenv("FS3D_DEBUG_FORCE_PUSH") != nullptr;   // timing experiments only
-        if (!rc && ns == 4) rc = launch_fused4(w, s);
+        if (!rc && ns == 4) rc = w->p2p ? fused4_pass_p2p(w) : launch_fused4(w, s);
         else if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, (w->p2p || force_push) ? 1 : 0);
         if (rc) return rc;
         // every warp of an edge pair adds the iterations it finished: nit of this pass x warps per pair
-        if (w->p2p) w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
+        if (w->p2p && ns != 4) { w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx); w->far_valid = false; }
     } else if (w->p2p) {
         // one process, one slab per GPU, peer access both ways: the same fused halo push as between ranks — one
         // kernel per slab per pass, edge planes stored straight into the neighbour's ghost plane over NVLink
-        for (auto &s : w->slabs) {
-            FS3D_CUDA(cudaSetDevice(s.device));
-            PairLayout L = pair_layout(s, hoff);
-            int rc = launch_skip_map(w, s);
-            if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, 1);
+        if (ns == 4) {
+            int rc = fused4_pass_p2p(w);
             if (rc) return rc;
+        } else {
+            for (auto &s : w->slabs) {
+                FS3D_CUDA(cudaSetDevice(s.device));
+                PairLayout L = pair_layout(s, hoff);
+                int rc = launch_skip_map(w, s);
+                if (!rc) rc = launch_pairs(w, s, 0, L.npairs, ns, 1);
+                if (rc) return rc;
+            }
+            w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
+            w->far_valid = false;
         }
-        w->wait_target += (unsigned long long)(w->desc.ny / 2 + (uint32_t)ns) * warps_per_pair(w->jidx);
     } else {
         // 1. edge pairs of every slab, 2. halo copies on the comm streams, 3. interiors
         for (auto &s : w->slabs) {
@@ -1725,6 +1781,21 @@ int fs3d_slab_attach_local(fs3d_world *w, fs3d_world *lower, fs3d_world *upper) 
     return FS3D_OK;
 }
 
+/* Four-step passes on a multi-process slab world need every rank's slab to support them (even internal boundaries,
+ * at least four planes, rows of 1024 or 2048 voxels, schedule version 1, no skipping): ranks ask fs3d_slab_can_fuse4,
+ * combine the answers (all-reduce AND) and call fs3d_slab_allow_fuse4 with the result before the first fs3d_step. */
+int fs3d_slab_can_fuse4(fs3d_world *w) {
+    if (!w || w->slabs.size() != 1) return 0;
+    return slab_fuse4_capable(w, w->slabs[0]) ? 1 : 0;
+}
+
+int fs3d_slab_allow_fuse4(fs3d_world *w, int allow) {
+    if (!w) return fail(FS3D_ERR_INVALID_ARG, "world is NULL");
+    if (allow && !fs3d_slab_can_fuse4(w)) return fail(FS3D_ERR_UNSUPPORTED, "this slab cannot run four-step passes (fs3d_slab_can_fuse4)");
+    w->fuse4_allowed = allow != 0;
+    return FS3D_OK;
+}
+
 /* What the halo waits cost so far (and resets the counters): out[0] = ns spent waiting for a neighbour's arrival counter,
  * summed over the warps that really blocked; out[1] = the longest single wait; out[2] = number of blocking waits. */
 int fs3d_push_wait_stats(fs3d_world *w, uint64_t out[3]) {
@@ -1758,6 +1829,7 @@ int fs3d_slab_push_halos(fs3d_world *w) {
         FS3D_CUDA(cudaMemcpyAsync(s.peer_hi.buf[w->cur], s.buf[w->cur] + pb * (size_t)s.nzl, pb, cudaMemcpyDefault, s.s_main));
     FS3D_CUDA(cudaStreamSynchronize(s.s_main));
     w->ghosts_stale = false;
+    w->far_valid = false;            // only the near planes were copied: the next four-step pass refreshes the far ones
     return FS3D_OK;
 }
 

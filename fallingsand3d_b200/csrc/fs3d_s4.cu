@@ -1,5 +1,5 @@
-// fs3d_s4.cu — instantiations and launcher of the four-steps-per-pass kernel (step4_kernel.cuh).  A translation unit
-// of its own so that nvcc compiles it beside fs3d.cu and fs3d_v2.cu (--threads).
+// fs3d_s4.cu — instantiations and launchers of the four-steps-per-pass kernel and its halo delivery (step4_kernel.cuh).
+// A translation unit of its own so that nvcc compiles it beside fs3d.cu and fs3d_v2.cu (--threads).
 // No reference counterpart; call site: /root/reference/src/engine/engine.cpp:59-70.
 #include "step4_kernel.cuh"
 
@@ -7,20 +7,24 @@ namespace fs3d {
 
 constexpr int STEP4_THREADS = 256;
 
-// xw = warps per band (1: nx = 1024, 2: nx = 2048); grid = CTAs (one per SM: the kernel takes 212 KB of shared memory)
-cudaError_t step4_launch(int xw, const Step4Params &p, unsigned grid, cudaStream_t stream) {
-    cudaError_t e;
-    if (xw == 1) {
-        constexpr uint32_t smem = step4_smem_bytes<1, STEP4_THREADS>();
-        e = cudaFuncSetAttribute(step4_kernel<1, STEP4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        step4_kernel<1, STEP4_THREADS><<<grid, STEP4_THREADS, smem, stream>>>(p);
-    } else {
-        constexpr uint32_t smem = step4_smem_bytes<2, STEP4_THREADS>();
-        e = cudaFuncSetAttribute(step4_kernel<2, STEP4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        step4_kernel<2, STEP4_THREADS><<<grid, STEP4_THREADS, smem, stream>>>(p);
-    }
+template <int XW, int NBR>
+static cudaError_t launch_one(const Step4Params &p, unsigned grid, cudaStream_t stream) {
+    constexpr uint32_t smem = step4_smem_bytes<STEP4_THREADS>();
+    cudaError_t e = cudaFuncSetAttribute(step4_kernel<XW, NBR, STEP4_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    step4_kernel<XW, NBR, STEP4_THREADS><<<grid, STEP4_THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// xw = warps per band (1: nx = 1024, 2: nx = 2048); grid = CTAs (one per SM: the kernel takes 212 KB of shared memory);
+// nbr = the slab has z-neighbours (coherent loads, bounded waits on the arrival counters)
+cudaError_t step4_launch(int xw, int nbr, const Step4Params &p, unsigned grid, cudaStream_t stream) {
+    if (xw == 1) return nbr ? launch_one<1, 1>(p, grid, stream) : launch_one<1, 0>(p, grid, stream);
+    return nbr ? launch_one<2, 1>(p, grid, stream) : launch_one<2, 0>(p, grid, stream);
+}
+
+cudaError_t halo4_launch(const Halo4Params &h, cudaStream_t stream) {
+    halo4_kernel<<<HALO4_BLOCKS, 256, 0, stream>>>(h);
     return cudaGetLastError();
 }
 

@@ -15,8 +15,9 @@
 // Rows of 2048 voxels use two warps per band (XW = 2), which exchange the word-boundary cells of stage B's odd
 // x-offset through the tagged mailboxes of step_kernel.cuh.
 //
-// Used by fs3d_step for single-slab worlds (no halo push, no skipping) with nx = 1024 or 2048 when four steps remain and
-// the step index is a multiple of four; everything else keeps the two-step pass.  Results are identical by construction
+// Used by fs3d_step for worlds of schedule version 1 without skipping whose rows are 1024 or 2048 voxels wide, when four
+// steps remain and the step index is a multiple of four: single slabs, and z-slabs with fused-push neighbours (NBR = 1:
+// two ghost planes per side, delivered by halo4_kernel after the pass).  Everything else keeps the two-step pass.  Results are identical by construction
 // and tested against the oracle (every parity test with nx in {1024, 2048}, the full 2048^3 compare, bench digests).
 // No reference counterpart; call site: /root/reference/src/engine/engine.cpp:59-70.
 #pragma once
@@ -33,17 +34,62 @@ struct Step4Params {
     const uint8_t *src;
     uint8_t *dst;
     uint32_t nx, ny, wpr;
-    uint32_t nzl;                  // owned planes; the slab is the whole grid (z0 = 0), local plane 0 / nzl+1 are STONE ghosts
+    uint32_t z0;                   // global z of local plane 1 (even)
+    uint32_t nzl;                  // owned planes (local 1 .. nzl); local plane 0 / nzl+1 are the near ghosts
     uint32_t nA, nB;               // stage-A pairs a: local planes (1+2a, 2+2a); stage-B pairs q: local planes (2q, 2q+1)
     uint32_t nbands;               // ceil(nB / S4_P)
     uint32_t nit;                  // march iterations: ny / 2 + 4
     uint32_t key_xy[4], key_zy[4]; // SCHEDULE.md §3 keys of steps t .. t+3
+    // z-slabs (NBR = 1 instantiations): a neighbour holds the planes below / above.  Stage B's pair across a slab boundary
+    // needs the neighbour's edge row AFTER stage A, so the neighbour's edge A-pair is recomputed here from TWO ghost
+    // planes per side: the near ghosts (local planes 0 and nzl+1) and the far ghosts, which live behind the slab in the
+    // same buffer — local plane nzl+2 = global z1+1 (so A-pair nA is contiguous) and local plane nzl+3 = global z0-2.
+    // halo4_kernel delivers all four after every four-step pass and bumps the arrival counters of step_kernel.cuh.
+    int has_lo, has_hi;
+    const unsigned long long *my_flags;   // arrive[0] (from below), arrive[1] (from above)
+    unsigned long long wait_target;
+    unsigned long long *push_err;
+    unsigned long long push_timeout_ns;
 };
 
-template <int XW, int THREADS>
+// Delivers this slab's two edge rows on each side into the z-neighbours' near and far ghost planes (peer memory) and
+// adds gridDim.x to their arrival counters.  near = 0: only the far planes (refresh before a four-step pass that follows
+// two-step passes, whose kernels push the near planes themselves).
+struct Halo4Params {
+    const uint8_t *src;            // my buffer (the one the neighbours will read ghosts of)
+    uint8_t *lo_buf, *hi_buf;      // the same buffer of the neighbour below / above, or nullptr
+    uint32_t nzl, lo_nzl, hi_nzl;
+    uint64_t plane_bytes;
+    unsigned long long *lo_flag, *hi_flag;   // neighbour below: its arrive[1]; above: its arrive[0]
+    int near;
+};
+constexpr unsigned HALO4_BLOCKS = 32;
+static __global__ void halo4_kernel(const Halo4Params h) {
+    const uint64_t n16 = h.plane_bytes / 16;
+    auto copy = [&](const uint8_t *s, uint8_t *d) {
+        for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < n16; v += (uint64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<uint4 *>(d)[v] = reinterpret_cast<const uint4 *>(s)[v];
+    };
+    if (h.lo_buf) {    // the neighbour below reads my planes 1 (z0) and 2 (z0+1) as its near ghost-high and far ghost-high
+        if (h.near) copy(h.src + 1 * h.plane_bytes, h.lo_buf + (uint64_t)(h.lo_nzl + 1) * h.plane_bytes);
+        copy(h.src + 2 * h.plane_bytes, h.lo_buf + (uint64_t)(h.lo_nzl + 2) * h.plane_bytes);
+    }
+    if (h.hi_buf) {    // the neighbour above reads my planes nzl (z1-1) and nzl-1 (z1-2) as its near ghost-low and far ghost-low
+        if (h.near) copy(h.src + (uint64_t)h.nzl * h.plane_bytes, h.hi_buf);
+        copy(h.src + (uint64_t)(h.nzl - 1) * h.plane_bytes, h.hi_buf + (uint64_t)(h.hi_nzl + 3) * h.plane_bytes);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (h.lo_flag) atomicAdd_system(h.lo_flag, 1ull);
+        if (h.hi_flag) atomicAdd_system(h.hi_flag, 1ull);
+    }
+}
+
+template <int THREADS>
 constexpr uint32_t step4_smem_bytes() { return (THREADS / 32) * S4_WORDS_PER_LANE * 32u * 4u; }
 
-template <int XW, int THREADS>
+template <int XW, int NBR, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) {
     using R = Rules1;
     using Cell = P2;
@@ -114,15 +160,26 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
         R::zy(up[0], up[1], lw[0], lw[1], hash_word(key + hzy + yu * HC2));
     };
 
+    // A-pairs that exist: -1 and nA are the neighbours' edge pairs, read from the ghost planes
+    const int a_first = (NBR && p.has_lo) ? -1 : 0, a_last = (int)p.nA - 1 + ((NBR && p.has_hi) ? 1 : 0);
+
     while (pos < end) {
-        const uint32_t band = (uint32_t)(pos / p.nit);
+        uint32_t band = (uint32_t)(pos / p.nit);
         const uint32_t it_a = (uint32_t)(pos - (uint64_t)band * p.nit);
+        // with neighbours the two edge bands come LAST: they wait for the neighbours' deliveries of the previous pass
+        if (NBR && p.nbands >= 3u) band = band < p.nbands - 2u ? band + 1u : (band == p.nbands - 2u ? 0u : p.nbands - 1u);
         const uint64_t left = end - pos;
         const uint32_t it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
         pos += it_b - it_a;
 
         const int qa = (int)(band * S4_P);
         const int nq = min(S4_P, (int)p.nB - qa);                 // B-pairs of this band; its A-pairs are a = qa-1 .. qa-1+nq
+        if (NBR) {
+            // bands that read ghost planes wait (bounded) until the neighbour delivered them after its previous pass
+            if (p.has_lo && qa == 0) wait_arrival(p.my_flags + 0, p.wait_target, p.push_err, p.push_timeout_ns, 0u);
+            if (p.has_hi && qa - 1 + nq >= (int)p.nA) wait_arrival(p.my_flags + 1, p.wait_target, p.push_err, p.push_timeout_ns, 1u);
+            __syncwarp();
+        }
         const uint32_t warm = it_a < S4_LEAD ? it_a : S4_LEAD;
         const uint32_t it0 = it_a - warm;
         // fresh pipelines: STONE below the segment's first plane (exact at the floor, rebuilt by the warm-up elsewhere)
@@ -136,15 +193,20 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
         Raw<1> raw;
         auto issue = [&](int kk, uint32_t itt) {
             const int a = qa - 1 + kk;
-            const bool ok = a >= 0 && a < (int)p.nA;
-            const uint8_t *base = p.src + (ok ? (size_t)(1 + 2 * a) * plane_bytes + (size_t)xw * 32u : (size_t)0);
+            const bool ok = a >= a_first && a <= a_last;
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
+            for (int r = 0; r < 2; ++r) {
+                // local plane 1 + 2a + r; plane -1 (global z0 - 2) is the far ghost kept at local plane nzl + 3
+                const int pl = 1 + 2 * a + r;
+                const uint8_t *base = p.src + (ok ? (size_t)(pl < 0 ? (int)p.nzl + 3 : pl) * plane_bytes + (size_t)xw * 32u : (size_t)0);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint32_t y = 2u * itt + h;
-                    ld256(base + (size_t)r * plane_bytes + (size_t)(y < ylast ? y : ylast) * row_bytes, raw.w[0][r][h]);
+                    const uint8_t *ad = base + (size_t)(y < ylast ? y : ylast) * row_bytes;
+                    if (NBR) ld256_coherent(ad, raw.w[0][r][h]);     // ghost planes are written by a peer GPU
+                    else ld256(ad, raw.w[0][r][h]);
                 }
+            }
         };
         issue(0, it0);
 
@@ -152,10 +214,11 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
             const uint32_t ie = ib + S4_K < it_b ? ib + S4_K : it_b;
             for (int k = 0; k <= nq; ++k) {
                 const int a = qa - 1 + k, q = qa + k - 1;          // stage-A pair loaded now; stage-B pair finished now (k >= 1)
-                const bool a_ok = a >= 0 && a < (int)p.nA;
-                const uint32_t hxyA[2] = {xw * HC1 + (uint32_t)(2 * a) * HC3, xw * HC1 + (uint32_t)(2 * a + 1) * HC3};
+                const bool a_ok = a >= a_first && a <= a_last;
+                // hash coordinates are GLOBAL: local plane pl is global z0 + pl - 1
+                const uint32_t hxyA[2] = {xw * HC1 + (p.z0 + (uint32_t)(2 * a)) * HC3, xw * HC1 + (p.z0 + (uint32_t)(2 * a + 1)) * HC3};
                 const uint32_t hzyA = hxyA[0];
-                const uint32_t hxyB[2] = {xw * HC1 + (uint32_t)(2 * q - 1) * HC3, xw * HC1 + (uint32_t)(2 * q) * HC3};
+                const uint32_t hxyB[2] = {xw * HC1 + (p.z0 + (uint32_t)(2 * q - 1)) * HC3, xw * HC1 + (p.z0 + (uint32_t)(2 * q)) * HC3};
                 const uint32_t hzyB = hxyB[0];
                 const bool own[2] = {k >= 1 && 2 * q >= 1 && 2 * q <= (int)p.nzl, k >= 1 && 2 * q + 1 <= (int)p.nzl};
                 uint8_t *const drow0 = p.dst + (size_t)(k >= 1 ? 2 * q : 0) * plane_bytes + (size_t)xw * 32u;

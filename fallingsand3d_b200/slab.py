@@ -163,6 +163,11 @@ class SlabWorld:
             lo = blobs[self.rank - 1] if self.rank > 0 else None
             hi = blobs[self.rank + 1] if self.rank + 1 < self.world_size else None
             self.engine.ipc_attach(lo, hi)
+            # four-step passes only if EVERY rank's slab supports them: the ranks must fuse alike
+            can = torch.tensor([1 if self.engine.world.slab_can_fuse4() else 0], device=self.engine.reduce_device())
+            dist.all_reduce(can, op=dist.ReduceOp.MIN, group=self.group)
+            self.fuse4 = bool(can.item())
+            self.engine.world.slab_allow_fuse4(self.fuse4)
             dist.barrier(group=self.group)
             self.p2p = True
         if self.world_size > 1:

@@ -291,6 +291,12 @@ class VoxelWorld:
         hi = C.create_string_buffer(upper_blob, self.IPC_BLOB_BYTES) if upper_blob is not None else None
         _check(self._lib.fs3d_slab_ipc_attach(self._h, lo, hi))
 
+    def slab_can_fuse4(self):
+        return bool(self._lib.fs3d_slab_can_fuse4(self._h))
+
+    def slab_allow_fuse4(self, allow):
+        _check(self._lib.fs3d_slab_allow_fuse4(self._h, 1 if allow else 0))
+
     def push_wait_stats(self):
         """(ns blocked on neighbours' arrival counters summed over warps, longest single wait ns, blocking waits); resets."""
         v = (C.c_uint64 * 3)()

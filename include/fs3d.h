@@ -260,6 +260,12 @@ int  fs3d_slab_ipc_attach(fs3d_world *w, const void *lower_blob, const void *upp
  * boundary.  Call it on every slab world, then fs3d_slab_push_halos on every one, before the first fs3d_step. */
 int  fs3d_slab_attach_local(fs3d_world *w, fs3d_world *lower, fs3d_world *upper);
 int  fs3d_slab_push_halos(fs3d_world *w);
+/* Four-step passes (FS3D_FLAG_NO_FUSE4 off) on a multi-process slab world: every rank's slab must support them (even
+ * internal boundaries, >= 4 planes, rows of 1024 / 2048 voxels, schedule version 1, no skipping) and all ranks must
+ * decide alike: combine fs3d_slab_can_fuse4 over the ranks (AND) and pass the result to fs3d_slab_allow_fuse4 before
+ * the first fs3d_step.  Default for slab worlds: not allowed (two-step passes).  In-process worlds decide by themselves. */
+int  fs3d_slab_can_fuse4(fs3d_world *w);
+int  fs3d_slab_allow_fuse4(fs3d_world *w, int allow);
 /* Cost of inter-GPU skew: ns the PUSH kernels spent blocked on a neighbour's arrival counter since the last call
  * (out[0] summed over warps, out[1] longest single wait, out[2] number of blocking waits); resets the counters. */
 int  fs3d_push_wait_stats(fs3d_world *w, uint64_t out[3]);

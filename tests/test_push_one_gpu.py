@@ -34,7 +34,8 @@ def _split(nz, k):
 def test_inprocess_world_pushes_halos_on_one_device(fs3d, oracle, nslabs, dims, scene):
     nx, ny, nz = dims
     g = oracle.generate(nx, ny, nz, scene, 5)
-    with fs3d.VoxelWorld(nx, ny, nz, seed=9, devices=[0] * nslabs, flags=fs3d.FLAG_PEER_PUSH_SHARED_DEVICE) as w:
+    # FLAG_NO_FUSE4: this test is about the PUSH kernels of the one- and two-step passes (the four-step pass has its own below)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=9, devices=[0] * nslabs, flags=fs3d.FLAG_PEER_PUSH_SHARED_DEVICE | fs3d.FLAG_NO_FUSE4) as w:
         assert w.num_slabs == nslabs
         w.upload(g)
         t = 0
@@ -70,6 +71,9 @@ class LocalRanks:
         self.worlds = [fs3d.VoxelWorld(nx, ny, nz, seed=seed, flags=flags, slab=b) for b in self.bounds]
         for i, w in enumerate(self.worlds):
             w.slab_attach_local(self.worlds[i - 1] if i > 0 else None, self.worlds[i + 1] if i + 1 < k else None)
+        self.fuse4 = all(w.slab_can_fuse4() for w in self.worlds)      # what ranks settle with an all-reduce
+        for w in self.worlds:
+            w.slab_allow_fuse4(self.fuse4)
         self.push()
 
     def push(self):
@@ -162,5 +166,50 @@ def test_push_watchdog_names_the_stalled_neighbour(fs3d, monkeypatch):
         with pytest.raises(fs3d.Fs3dError):
             lo.step(2)                 # a failed world refuses to step
         lo.download()                  # but can still be inspected and destroyed
+    finally:
+        r.close()
+
+
+# ---- four steps per pass across slabs: two ghost planes per side, delivered by halo4_kernel after every pass ----
+@pytest.mark.parametrize("nslabs,dims,scene", [(2, (1024, 16, 12), 3), (3, (2048, 40, 26), 4), (4, (2048, 24, 16), 4), (3, (1024, 70, 30), 4),
+                                               (2, (2048, 9, 9), 3)])
+def test_inprocess_world_four_step_passes_on_one_device(fs3d, oracle, nslabs, dims, scene):
+    nx, ny, nz = dims
+    g = oracle.generate(nx, ny, nz, scene, 5)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=9, devices=[0] * nslabs, flags=fs3d.FLAG_PEER_PUSH_SHARED_DEVICE) as w:
+        w.upload(g)
+        t = 0
+        # four-step passes; a far-ghost refresh after one- and two-step passes and after an edit; long runs without a host sync
+        for n in (4, 8, 1, 2, 5, 40, 3, 80, 4):
+            ms, launches = w.step_timed(n)
+            oracle.run(g, 9, t, n)
+            t += n
+            assert w.digest() == oracle.digest(g), f"step {t}"
+            if n == 40:
+                w.set_cell(5, ny - 1, nz // 2, fs3d.SAND)
+                g[nz // 2, ny - 1, 5] = 1
+        assert np.array_equal(w.download(), g)
+    # the first four steps of a fresh world: one far-ghost refresh, one four-step kernel and one delivery per slab
+    with fs3d.VoxelWorld(2048, 24, 16, seed=1, devices=[0] * 4, flags=fs3d.FLAG_PEER_PUSH_SHARED_DEVICE) as w:
+        w.generate(fs3d.SCENE_MIXED_NOISE, 1)
+        assert w.step_timed(4)[1] == 3 * 4
+        assert w.step_timed(8)[1] == 2 * 2 * 4          # afterwards kernel + delivery
+
+
+@pytest.mark.parametrize("k,dims,scene", [(2, (1024, 32, 20), 4), (3, (2048, 48, 26), 4), (3, (1024, 9, 14), 3)])
+def test_attached_slab_worlds_four_step_passes(fs3d, oracle, k, dims, scene):
+    nx, ny, nz = dims
+    g = oracle.generate(nx, ny, nz, scene, 3)
+    r = LocalRanks(fs3d, nx, ny, nz, k, seed=5)
+    try:
+        assert r.fuse4
+        r.upload(g)
+        t = 0
+        for n in (80, 1, 2, 3, 40, 7, 4):
+            r.step(n)
+            oracle.run(g, 5, t, n)
+            t += n
+            assert r.digest() == oracle.digest(g), f"step {t}"
+        assert np.array_equal(r.download(), g)
     finally:
         r.close()
