@@ -308,7 +308,7 @@ def big_grid_block(args, world_size, rank, hbm_peak):
             frame_ms = (time.perf_counter() - t0) * 1e3
             assert np.array_equal(sw.histogram(), h0), "material counts changed: invalid run"
             digest = sw.digest()
-            launches = (1 if sw.p2p else 3) * ((K + 1) // 2)
+            launches = sw.engine.world.kernel_launches if sw.p2p else 3 * ((K + 1) // 2)
             sw.close()
     except Exception as e:                                  # the main line must still be printed
         return {"failed": repr(e)[:200]}
@@ -440,11 +440,13 @@ def ours(args):
         sampler.mark()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st = sw.engine.stream
+        l0 = sw.engine.world.kernel_launches
         ev0.record(st)
         sw.step(K)
         ev1.record(st)
         sw.sync()
         torch.cuda.synchronize()
+        launches = sw.engine.world.kernel_launches - l0 if sw.p2p else 3 * ((K + 1) // 2)     # this rank's kernels (NCCL's own not counted)
         t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -457,18 +459,21 @@ def ours(args):
             wmax = ws.clone()
             dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(ws, op=dist.ReduceOp.SUM)
-            passes = (K + 1) // 2
+            fuse4 = bool(getattr(sw, "fuse4", False))
+            passes = (K + 3) // 4 if fuse4 else (K + 1) // 2
             npairs = (sw.z_end - sw.z_begin) // 2 + 1
-            warps = 148 * 8
+            if fuse4:       # bands of 6 pairs, one segment per unit (8 warps per SM, n / 1024 warps per unit), 7 warm-up iterations
+                segs, work = 148 * 8 // max(1, n // 1024), -(-npairs // 6) * (n // 2 + 4)
+                lead = min(1.0, 7.0 * segs / work)
+            else:
+                lead = min(1.0, 3.0 * 148 * 8 / (npairs * (n // 2 + 2)))
             halo_wait = {"longest_single_wait_ms": float(wmax[1].item()) / 1e6, "blocking_waits_all_ranks": int(ws[2].item()),
                          "blocked_warp_ms_per_pass_worst_rank": float(wmax[0].item()) / 1e6 / passes,
-                         "lead_in_share_of_iterations": min(1.0, 3.0 * warps / (npairs * (n // 2 + 2))),
-                         "note": "PUSH kernels: warps of a slab's two edge pairs wait (bounded) for the neighbour's previous "
-                                 "pass; lead-in = 3 re-computed iterations per march segment, one segment per resident warp"}
+                         "steps_per_pass": 4 if fuse4 else 2, "lead_in_share_of_iterations": lead,
+                         "note": "warps of a slab's edge pairs / bands wait (bounded) for the neighbour's previous pass; lead-in = "
+                                 "re-computed iterations per march segment (3 with two steps per pass, 7 with four)"}
         assert np.array_equal(sw.histogram(), h0), "material counts changed: invalid run"
         digest = sw.digest()
-        # kernels per pass per rank: 2 edge launches + 1 interior (NCCL's own kernels not counted); 2 steps per pass
-        launches = (1 if sw.p2p else 3) * ((K + 1) // 2)
 
     value = voxels * K / (ms * 1e-3)
     achieved = 2.0 * voxels * K / (ms * 1e-3) / 1e9 / world_size     # per-GPU algorithmic GB/s
@@ -591,7 +596,9 @@ def ours(args):
                                f"generated on device, skipping off",
                    "grid": [n, n, n],
                    "parallelism": ("single GPU" if world_size == 1 else
-                                   f"z-slabs x{world_size}, halo pushed over NVLink peer memory inside the step kernel" if p2p else
+                                   (f"z-slabs x{world_size}, four steps per pass, two ghost planes per side delivered over NVLink peer memory "
+                                    f"by a kernel behind each pass" if getattr(sw, "fuse4", False) else
+                                    f"z-slabs x{world_size}, halo pushed over NVLink peer memory inside the step kernel") if p2p else
                                    f"z-slabs x{world_size}, halo planes exchanged with NCCL send/recv on a side stream"),
                    "l2": "inputs larger than L2 (grid %.1f GiB per buffer vs 126 MB L2); no flush" % (voxels / 2**30),
                    "digest": hex(digest), "digest_step": total_steps, "digest_check": digest_check},

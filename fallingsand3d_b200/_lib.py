@@ -53,6 +53,7 @@ SIGNATURES = {
     "fs3d_download": (C.c_int, [_W, C.c_void_p]),
     "fs3d_step": (C.c_int, [_W, C.c_uint32]),
     "fs3d_sync": (C.c_int, [_W]),
+    "fs3d_kernel_launches": (C.c_int, [_W, C.POINTER(C.c_uint64)]),
     "fs3d_step_index": (C.c_int, [_W, C.POINTER(C.c_uint64)]),
     "fs3d_step_timed": (C.c_int, [_W, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]),
     "fs3d_step_host": (C.c_int, [_W, C.c_void_p, C.c_void_p, C.c_uint32]),

@@ -1077,6 +1077,12 @@ int fs3d_sync(fs3d_world *w) {
     return sync_all(w);
 }
 
+int fs3d_kernel_launches(fs3d_world *w, uint64_t *out) {
+    if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
+    *out = w->launches;
+    return FS3D_OK;
+}
+
 int fs3d_step_index(fs3d_world *w, uint64_t *out) {
     if (!w || !out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
     *out = w->step;

@@ -147,6 +147,12 @@ class VoxelWorld:
         _check(self._lib.fs3d_step_index(self._h, C.byref(out)))
         return out.value
 
+    @property
+    def kernel_launches(self):
+        out = C.c_uint64()
+        _check(self._lib.fs3d_kernel_launches(self._h, C.byref(out)))
+        return out.value
+
     def step_timed(self, n=1):
         """Runs n steps; returns (device milliseconds from CUDA events on the step stream, kernels launched)."""
         ms = C.c_float()

@@ -180,6 +180,7 @@ int  fs3d_download(fs3d_world *w, uint8_t *host);
 int  fs3d_step(fs3d_world *w, uint32_t n_steps);          /* asynchronous */
 int  fs3d_sync(fs3d_world *w);
 int  fs3d_step_index(fs3d_world *w, uint64_t *out);
+int  fs3d_kernel_launches(fs3d_world *w, uint64_t *out);   /* kernels this world has launched since it was created */
 /* Runs n_steps and returns the device time between CUDA events recorded on the step stream
  * (max over slabs).  kernel_launches, if non-NULL, receives the number of kernels launched. */
 int  fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kernel_launches);
