@@ -586,7 +586,9 @@ def ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get(f"{n}_fused") if world_size == 1 else None
+            tj = json.load(f)
+            # the dominant kernel of the N = 1 run: the four-step kernel where fs3d_step uses it (rows of 1024 / 2048 voxels)
+            traffic = (tj.get(f"{n}_fused4") if n in (1024, 2048) else tj.get(f"{n}_fused")) if world_size == 1 else None
 
     line = {
         "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": world_size, "steps": K, "warmup": Wm,

@@ -50,10 +50,13 @@ def main():
     out = {"2048": traffic.get("single_2048", old.get("2048")), "2048_fused": traffic.get("fused_2048", old.get("2048_fused")),
            "4096x4096x512": traffic.get("single_4096w", old.get("4096x4096x512")),
            "4096x4096x512_fused": traffic.get("fused_4096w", old.get("4096x4096x512_fused")),
+           "2048_fused4": traffic.get("fused4_2048", old.get("2048_fused4")),
+           "1024_fused4": traffic.get("fused4_1024", old.get("1024_fused4")),
            "source": f"profiles/{tag}_*_ncu_full_raw.csv (entries this tag did not capture are kept from the earlier round's r01e_*): dram__bytes_read.sum + dram__bytes_write.sum per launch "
                      "(mean over the captured launches: both x-offsets, and both step parities for the single-step "
                      "kernels). 2048 = 2048^3 grid, 17.18 GB algorithmic per single-step launch; a fused launch "
-                     "advances two steps (34.36 GB algorithmic by the 2 B/update definition) on the same traffic. "
+                     "advances two steps (34.36 GB algorithmic by the 2 B/update definition) on the same traffic; a fused4 launch (step4_kernel) "
+                     "advances FOUR steps and reads 7/6 of the grid (the first z-pair of every band of six is loaded twice). "
                      "4096x4096x512 = one rank's slab of 4096^3 on 8 GPUs (warp-pair kernels), same voxel count"}
     with open(tp, "w") as f:
         json.dump(out, f, indent=1)
