@@ -569,6 +569,8 @@ static int launch_fused4(fs3d_world *w, Slab &s) {
     p.has_hi = s.peer_hi.valid ? 1 : 0;
     p.my_flags = s.d_flags; p.wait_target = w->wait_target;
     p.push_err = s.d_flags + 2; p.push_timeout_ns = w->push_timeout_ns;
+    static const bool edge_early = std::getenv("FS3D_S4_EDGE_EARLY") != nullptr;      // A/B switch
+    p.edge_late = edge_early ? 0 : 1;
     const int xw = (int)(p.wpr / 32);
     // one CTA per SM, but never fewer than ~16 iterations per unit
     const uint64_t total = (uint64_t)p.nbands * p.nit;

@@ -50,6 +50,7 @@ struct Step4Params {
     unsigned long long wait_target;
     unsigned long long *push_err;
     unsigned long long push_timeout_ns;
+    int edge_late;                 // NBR: units take their share of the two edge bands AFTER their share of the interior bands
 };
 
 // Delivers this slab's two edge rows on each side into the z-neighbours' near and far ghost planes (peer memory) and
@@ -117,9 +118,29 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
     const bool hasp = xw > 0u, hasn = xw + 1u < p.wpr;
     const size_t row_bytes = p.nx, plane_bytes = (size_t)p.nx * p.ny;
     const uint32_t ylast = p.ny - 1u;
+    // Work split.  The (band x iteration) space is cut into contiguous spans, one per unit.  With neighbours the two edge
+    // bands (permuted to the end of the position order) must wait for the neighbours' deliveries of the previous pass: a
+    // unit that owned a span of an edge band would wait at the very start of the kernel, putting every bit of inter-GPU
+    // skew on the critical path.  So (edge_late) the edge bands are cut into chunks that some units take as a SECOND span
+    // behind a correspondingly shorter interior span: edge work starts in the second half of the kernel and skew up
+    // to that much costs nothing.
     const uint64_t total = (uint64_t)p.nbands * p.nit;
-    uint64_t pos = total * gw / nw;
-    const uint64_t end = total * (gw + 1) / nw;
+    uint64_t lo0 = total * gw / nw, hi0 = total * (gw + 1) / nw, lo1 = 0, hi1 = 0;     // first span, second span (edge chunk)
+    if (NBR && p.edge_late && p.nbands >= 3u) {
+        const uint64_t I = (uint64_t)(p.nbands - 2u) * p.nit, E = 2ull * p.nit, U = nw;
+        const uint64_t t0 = total / U, et = t0 / 2 > 16 ? t0 / 2 : 16;
+        uint64_t C = (E + et - 1) / et;
+        C = C < 1 ? 1 : (C > U ? U : C);
+        const uint64_t y = (I + E + S4_LEAD * C) / U, ec = E / C + S4_LEAD;
+        const uint64_t x = y > ec ? y - ec : 0;                    // interior share of a unit that also takes an edge chunk
+        const uint64_t cx = C * x < I ? C * x : I;
+        auto S = [&](uint64_t u) -> uint64_t {
+            if (C >= U) return I * u / U;
+            return u <= C ? (u * x < I ? u * x : I) : cx + (I - cx) * (u - C) / (U - C);
+        };
+        lo0 = S(gw); hi0 = S(gw + 1);
+        if (gw < C) { lo1 = I + E * gw / C; hi1 = I + E * (gw + 1) / C; }
+    }
 
     // one-way message between the two warps of a unit (see step_kernel.cuh)
     auto xmail = [&](uint32_t from_half, uint32_t from_lane, uint32_t payload) -> uint32_t {
@@ -163,6 +184,9 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
     // A-pairs that exist: -1 and nA are the neighbours' edge pairs, read from the ghost planes
     const int a_first = (NBR && p.has_lo) ? -1 : 0, a_last = (int)p.nA - 1 + ((NBR && p.has_hi) ? 1 : 0);
 
+    for (int sp = 0; sp < 2; ++sp) {
+    uint64_t pos = sp == 0 ? lo0 : lo1;
+    const uint64_t end = sp == 0 ? hi0 : hi1;
     while (pos < end) {
         uint32_t band = (uint32_t)(pos / p.nit);
         const uint32_t it_a = (uint32_t)(pos - (uint64_t)band * p.nit);
@@ -264,7 +288,11 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
                     Cell L3 = {sH(slot, 0), sH(slot, 1)}, L2 = {sH(slot, 2), sH(slot, 3)};
                     sH(slot, 0) = c3[1].p0; sH(slot, 1) = c3[1].p1; sH(slot, 2) = c2[1].p0; sH(slot, 3) = c2[1].p1;
 
-                    if (k >= 1) {
+                    // a segment that starts in mid-grid warms up for 7 iterations; stage A's planes are not right before the
+                    // fourth, so stage B only idles through the first three (its pipeline converges from any state in 3)
+                    if (k >= 1 && warm == S4_LEAD && it < it0 + 3u) {
+                        bprev[0] = L2; bprev[1] = c2[0];
+                    } else if (k >= 1) {
                         // ---- stage B: steps t+2 (XY then ZY) and t+3 (ZY then XY), x-offset 1, on rows (pair a-1's r1, pair a's r0)
                         // its plane pair is (y1-4, y1-3): the even plane waited one iteration in `bprev`
                         Cell loB[2] = {bprev[0], bprev[1]}, hiB[2] = {L3, c3[0]};
@@ -307,6 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
                 }
             }
         }
+    }
     }
 }
 
