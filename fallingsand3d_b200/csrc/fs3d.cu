@@ -569,8 +569,11 @@ static int launch_fused4(fs3d_world *w, Slab &s) {
     p.has_hi = s.peer_hi.valid ? 1 : 0;
     p.my_flags = s.d_flags; p.wait_target = w->wait_target;
     p.push_err = s.d_flags + 2; p.push_timeout_ns = w->push_timeout_ns;
-    static const bool edge_early = std::getenv("FS3D_S4_EDGE_EARLY") != nullptr;      // A/B switch
-    p.edge_late = edge_early ? 0 : 1;
+    // Edge bands as a late second span: removes every blocking wait (profiles/r02l_bench_n{4,8}.json: 0 waits) but pays a
+    // second warm-up on ~100 units — measured 1-2 % slower at N = 4 and 8 than letting the edge units wait at the start
+    // (r02l_bench_n{4,8}_edge_early.json), so it is opt-in: useful when ranks are badly skewed.
+    static const bool edge_late = std::getenv("FS3D_S4_EDGE_LATE") != nullptr;
+    p.edge_late = edge_late ? 1 : 0;
     const int xw = (int)(p.wpr / 32);
     // one CTA per SM, but never fewer than ~16 iterations per unit
     const uint64_t total = (uint64_t)p.nbands * p.nit;

@@ -5,7 +5,10 @@
 
 namespace fs3d {
 
-constexpr int STEP4_THREADS = 256;
+#ifndef FS3D_S4_THREADS
+#define FS3D_S4_THREADS 256
+#endif
+constexpr int STEP4_THREADS = FS3D_S4_THREADS;
 
 template <int XW, int NBR>
 static cudaError_t launch_one(const Step4Params &p, unsigned grid, cudaStream_t stream) {

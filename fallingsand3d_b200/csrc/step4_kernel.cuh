@@ -25,8 +25,14 @@
 
 namespace fs3d {
 
-constexpr int S4_P = 6;            // B-pairs per band
-constexpr int S4_K = 8;            // iterations per y-block
+#ifndef FS3D_S4_P
+#define FS3D_S4_P 6
+#endif
+#ifndef FS3D_S4_K
+#define FS3D_S4_K 8
+#endif
+constexpr int S4_P = FS3D_S4_P;    // B-pairs per band        (tuning hooks: profiles/r02m_experiments_step4.txt)
+constexpr int S4_K = FS3D_S4_K;    // iterations per y-block
 constexpr uint32_t S4_LEAD = 7;    // warm-up iterations that rebuild both stages' carried planes
 constexpr uint32_t S4_WORDS_PER_LANE = (S4_P + 1) * 12 + S4_P * 16 + S4_K * 4;     // A states, B states, hand-off buffer
 
