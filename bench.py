@@ -462,8 +462,8 @@ def ours(args):
             fuse4 = bool(getattr(sw, "fuse4", False))
             passes = (K + 3) // 4 if fuse4 else (K + 1) // 2
             npairs = (sw.z_end - sw.z_begin) // 2 + 1
-            if fuse4:       # bands of 6 pairs, one segment per unit (8 warps per SM, n / 1024 warps per unit), 7 warm-up iterations
-                segs, work = 148 * 8 // max(1, n // 1024), -(-npairs // 6) * (n // 2 + 4)
+            if fuse4:       # bands of 4 pairs, one segment per unit (12 warps per SM, n / 1024 warps per unit), 7 warm-up iterations
+                segs, work = 148 * 12 // max(1, n // 1024), -(-npairs // 4) * (n // 2 + 4)
                 lead = min(1.0, 7.0 * segs / work)
             else:
                 lead = min(1.0, 3.0 * 148 * 8 / (npairs * (n // 2 + 2)))

@@ -6,7 +6,7 @@
 namespace fs3d {
 
 #ifndef FS3D_S4_THREADS
-#define FS3D_S4_THREADS 256
+#define FS3D_S4_THREADS 384
 #endif
 constexpr int STEP4_THREADS = FS3D_S4_THREADS;
 
@@ -19,7 +19,7 @@ static cudaError_t launch_one(const Step4Params &p, unsigned grid, cudaStream_t 
     return cudaGetLastError();
 }
 
-// xw = warps per band (1: nx = 1024, 2: nx = 2048); grid = CTAs (one per SM: the kernel takes 212 KB of shared memory);
+// xw = warps per band (1: nx = 1024, 2: nx = 2048); grid = CTAs (one per SM: the kernel parks 210 KB of pipeline state in shared memory);
 // nbr = the slab has z-neighbours (coherent loads, bounded waits on the arrival counters)
 cudaError_t step4_launch(int xw, int nbr, const Step4Params &p, unsigned grid, cudaStream_t stream) {
     if (xw == 1) return nbr ? launch_one<1, 1>(p, grid, stream) : launch_one<1, 0>(p, grid, stream);

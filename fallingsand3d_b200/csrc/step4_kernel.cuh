@@ -5,8 +5,8 @@
 // under both steps (that is the two-step pass of step_kernel.cuh); between the stages the pairing shifts by one row, so
 // stage B's pair q = (plane 2q, 2q+1) takes the upper row of stage-A pair q−1 and the lower row of stage-A pair q.
 //
-// A warp stays autonomous (no barrier, no other warp's data): it owns a BAND of P consecutive B-pairs and walks the grid
-// in y-blocks of K iterations; inside a y-block it visits the band's P+1 A-pairs one after the other —
+// A warp stays autonomous (no barrier, no other warp's data): it owns a BAND of P (= 4) consecutive B-pairs and walks the
+// grid in y-blocks of K (= 4) iterations; inside a y-block it visits the band's P+1 A-pairs one after the other —
 //     load pair a  →  stage A (two steps)  →  its upper row's finished planes go into a K-deep shared-memory buffer,
 //     stage B (two more steps) on (the previous pair's upper row out of that buffer, this pair's lower row)  →  store
 // — and parks each pair's pipeline state (the carried planes of both stages: 28 words per lane) in shared memory until
@@ -25,11 +25,15 @@
 
 namespace fs3d {
 
+// Band size P, y-block K and CTA size were chosen by A/B on a B200 (profiles/r02m_experiments_step4.txt): P = 4, K = 4
+// leaves 17.5 KB of parked state per warp, so TWELVE warps fit an SM (384-thread CTAs) instead of eight with P = 6,
+// K = 8 — 7 % faster at 2048^3 although 5/4 instead of 7/6 of stage A is recomputed (the kernel is ALU-bound and latency
+// hiding wins), the same at 1024^3.
 #ifndef FS3D_S4_P
-#define FS3D_S4_P 6
+#define FS3D_S4_P 4
 #endif
 #ifndef FS3D_S4_K
-#define FS3D_S4_K 8
+#define FS3D_S4_K 4
 #endif
 constexpr int S4_P = FS3D_S4_P;    // B-pairs per band        (tuning hooks: profiles/r02m_experiments_step4.txt)
 constexpr int S4_K = FS3D_S4_K;    // iterations per y-block
