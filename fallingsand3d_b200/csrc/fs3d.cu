@@ -580,6 +580,14 @@ static int launch_fused4(fs3d_world *w, Slab &s) {
     const uint64_t units = std::max<uint64_t>(1, total / 16);
     const uint64_t upc = step4_units_per_cta(xw);
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s.num_sms, (units + upc - 1) / upc));
+    // Group split with staggered units (step4_kernel.cuh): only where a CTA's span is long against the stagger, i.e. the
+    // big grids that are DRAM-heavy anyway.  FS3D_S4_GROUP_SPAN overrides the threshold (0 = never; tests use 1).
+    if (!p.has_lo && !p.has_hi) {
+        uint64_t min_span = 8ull * upc * S4_K;
+        if (const char *e = std::getenv("FS3D_S4_GROUP_SPAN")) { min_span = std::strtoull(e, nullptr, 10); if (min_span == 0) min_span = ~0ull; }
+        const uint64_t span = (uint64_t)((p.nbands + upc - 1) / upc) * p.nit / grid;
+        p.groups = span >= min_span ? 1 : 0;
+    }
     FS3D_CUDA(step4_launch(xw, (p.has_lo || p.has_hi) ? 1 : 0, p, grid, s.s_main));
     w->launches++;
     return FS3D_OK;

@@ -35,6 +35,9 @@ namespace fs3d {
 #ifndef FS3D_S4_K
 #define FS3D_S4_K 4
 #endif
+#ifndef FS3D_S4_ONE_ISSUE
+#define FS3D_S4_ONE_ISSUE 1      // one load-issue site per iteration instead of three (1 % faster, a tenth less code)
+#endif
 constexpr int S4_P = FS3D_S4_P;    // B-pairs per band        (tuning hooks: profiles/r02m_experiments_step4.txt)
 constexpr int S4_K = FS3D_S4_K;    // iterations per y-block
 constexpr uint32_t S4_LEAD = 7;    // warm-up iterations that rebuild both stages' carried planes
@@ -61,6 +64,7 @@ struct Step4Params {
     unsigned long long *push_err;
     unsigned long long push_timeout_ns;
     int edge_late;                 // NBR: units take their share of the two edge bands AFTER their share of the interior bands
+    int groups;                    // single slab: CTAs own spans of (group of neighbouring bands x iteration), units staggered
 };
 
 // Delivers this slab's two edge rows on each side into the z-neighbours' near and far ghost planes (peer memory) and
@@ -136,34 +140,36 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
     // to that much costs nothing.
     const uint64_t total = (uint64_t)p.nbands * p.nit;
     uint64_t lo0 = total * gw / nw, hi0 = total * (gw + 1) / nw, lo1 = 0, hi1 = 0;     // first span, second span (edge chunk)
-    if (NBR && p.edge_late && p.nbands >= 3u) {
-        const uint64_t I = (uint64_t)(p.nbands - 2u) * p.nit, E = 2ull * p.nit, U = nw;
-        const uint64_t t0 = total / U, et = t0 / 2 > 16 ? t0 / 2 : 16;
-        uint64_t C = (E + et - 1) / et;
-        C = C < 1 ? 1 : (C > U ? U : C);
-        const uint64_t y = (I + E + S4_LEAD * C) / U, ec = E / C + S4_LEAD;
-        const uint64_t x = y > ec ? y - ec : 0;                    // interior share of a unit that also takes an edge chunk
-        const uint64_t cx = C * x < I ? C * x : I;
-        auto S = [&](uint64_t u) -> uint64_t {
-            if (C >= U) return I * u / U;
-            return u <= C ? (u * x < I ? u * x : I) : cx + (I - cx) * (u - C) / (U - C);
-        };
-        lo0 = S(gw); hi0 = S(gw + 1);
-        if (gw < C) { lo1 = I + E * gw / C; hi1 = I + E * (gw + 1) / C; }
+    // Single slab with long spans (p.groups, set by the host): the units of a CTA take NEIGHBOURING bands and march the
+    // same iterations of them side by side, each one y-block (in y) behind the unit below it.  The A-pair two
+    // neighbouring bands both load — the lower band as its last pair, the upper one as its first — is then read twice
+    // within one pair-visit's time and the second read hits L2 (those loads say evict_last, all others evict_first):
+    // DRAM reads fall from 5/4 to 25/24 of the grid.  The CTA, not the unit, owns a contiguous span of the (group of
+    // UNITS bands x iteration) space; inner segment boundaries of unit `pic` move down by pic * K iterations, so a
+    // band's segments still tile [0, nit).  Without the stagger the second read comes four visits BEFORE the first one
+    // of the next y-block and misses (profiles/r02r_experiments_groups.txt).
+    const bool grp = !NBR && p.groups != 0;
+    if (grp) {
+        const uint64_t totalg = (uint64_t)((p.nbands + UNITS - 1u) / UNITS) * p.nit;
+        // equal spans, except that the last CTA's is (UNITS - 1) * K shorter: nothing follows the last group, so its
+        // top unit would otherwise run that much longer than every other unit of the grid
+        const uint64_t per = (totalg + (UNITS - 1u) * (uint64_t)S4_K + gridDim.x - 1u) / gridDim.x;
+        lo0 = per * blockIdx.x < totalg ? per * blockIdx.x : totalg;
+        hi0 = per * (blockIdx.x + 1u) < totalg ? per * (blockIdx.x + 1u) : totalg;
     }
 
     // one-way message between the two warps of a unit (see step_kernel.cuh)
     auto xmail = [&](uint32_t from_half, uint32_t from_lane, uint32_t payload) -> uint32_t {
         ++xseq;
-        const uint32_t tag = (xseq & 0x3FFFu) << 18;
+        const uint32_t tag = xseq << 28;
         volatile uint32_t *slot = xch + (xseq & 1u);
         if (half == from_half) {
-            if (lane == from_lane) *slot = tag | payload;
+            if (lane == from_lane) *slot = (payload & 0x0FFFFFFFu) | tag;
             return 0u;
         }
         uint32_t v;
-        do { v = *slot; } while ((v & 0xFFFC0000u) != tag);
-        return v & 0x3FFFFu;
+        do { v = *slot; } while ((v & 0xF0000000u) != tag);
+        return v;                                         // Rules1's edge bits tolerate the tag (bitslice.cuh, E-packing)
     };
     // XY sub-step on (upper, lower) of both rows; x-offset 0 (stage A) or 1 (stage B, cells of the word-straddling block
     // cross lanes by shuffle and the warp pair's boundary through the mailbox)
@@ -199,12 +205,20 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
     const uint64_t end = sp == 0 ? hi0 : hi1;
     while (pos < end) {
         uint32_t band = (uint32_t)(pos / p.nit);
-        const uint32_t it_a = (uint32_t)(pos - (uint64_t)band * p.nit);
+        uint32_t it_a = (uint32_t)(pos - (uint64_t)band * p.nit);
         // with neighbours the two edge bands come LAST: they wait for the neighbours' deliveries of the previous pass
         if (NBR && p.nbands >= 3u) band = band < p.nbands - 2u ? band + 1u : (band == p.nbands - 2u ? 0u : p.nbands - 1u);
         const uint64_t left = end - pos;
-        const uint32_t it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
+        uint32_t it_b = (left < (uint64_t)(p.nit - it_a)) ? it_a + (uint32_t)left : p.nit;
         pos += it_b - it_a;
+        if (grp) {
+            band = band * UNITS + pic;                 // `band` was the group
+            if (band >= p.nbands) continue;
+            const uint32_t sh = pic * (uint32_t)S4_K;
+            auto shifted = [&](uint32_t s) { return s == 0u ? 0u : (s >= p.nit ? p.nit : (s > sh ? s - sh : 0u)); };
+            it_a = shifted(it_a); it_b = shifted(it_b);
+            if (it_a >= it_b) continue;
+        }
 
         const int qa = (int)(band * S4_P);
         const int nq = min(S4_P, (int)p.nB - qa);                 // B-pairs of this band; its A-pairs are a = qa-1 .. qa-1+nq
@@ -228,6 +242,8 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
         auto issue = [&](int kk, uint32_t itt) {
             const int a = qa - 1 + kk;
             const bool ok = a >= a_first && a <= a_last;
+            // the pair the neighbouring band of this CTA loads too (grp)
+            const bool again = (kk == 0 && pic != 0u) || (kk == nq && pic + 1u != UNITS);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 // local plane 1 + 2a + r; plane -1 (global z0 - 2) is the far ghost kept at local plane nzl + 3
@@ -238,7 +254,9 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
                     const uint32_t y = 2u * itt + h;
                     const uint8_t *ad = base + (size_t)(y < ylast ? y : ylast) * row_bytes;
                     if (NBR) ld256_coherent(ad, raw.w[0][r][h]);     // ghost planes are written by a peer GPU
-                    else ld256(ad, raw.w[0][r][h]);
+                    else if (!grp) ld256(ad, raw.w[0][r][h]);
+                    else if (again) ld256_keep(ad, raw.w[0][r][h]);
+                    else ld256_once(ad, raw.w[0][r][h]);
                 }
             }
         };
@@ -283,9 +301,16 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
                     }
                     // the next plane pair's loads are in flight while this one is evaluated: next iteration of this pair,
                     // else the next pair's first, else the next y-block's first pair
+#if FS3D_S4_ONE_ISSUE
+                    {
+                        const bool more = it + 1u < ie, nextk = k < nq;
+                        if (more || nextk || ie < it_b) issue(more ? k : (nextk ? k + 1 : 0), more ? it + 1u : (nextk ? ib : ie));
+                    }
+#else
                     if (it + 1u < ie) issue(k, it + 1u);
                     else if (k < nq) issue(k + 1, ib);
                     else if (ie < it_b) issue(0, ie);
+#endif
 
                     // ---- stage A: steps t (XY then ZY) and t+1 (ZY then XY), x-offset 0
                     xy0(hi, lo, y1 + 1u, p.key_xy[0], hxyA);

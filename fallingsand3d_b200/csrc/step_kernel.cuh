@@ -36,7 +36,8 @@ namespace fs3d {
 struct Rules1 {
     using Cell = P2;
     static constexpr bool COLUMN_FORM = true;          // the per-column XY form (xy_substep) exists for two planes only
-    static constexpr uint32_t NB_STONE = 0xFFu;         // packed voxel-0 bits of a word beyond the wall
+    static constexpr uint32_t NB_STONE = NB_STONE2;     // packed voxel-0 bits of a word beyond the wall
+    static constexpr bool EDGE_TOLERANT = true;         // consumers of the packed edge bits ignore every other bit
     static __device__ __forceinline__ Cell stone() { return {ONES, ONES}; }
     static __device__ __forceinline__ Cell pack(const uint32_t (&w)[8]) { return fs3d::pack(w); }
     static __device__ __forceinline__ void unpack(Cell c, uint32_t (&w)[8]) { fs3d::unpack(c, w); }
@@ -53,6 +54,7 @@ struct Rules3 {
     using Cell = P3;
     static constexpr bool COLUMN_FORM = false;
     static constexpr uint32_t NB_STONE = NB_STONE3;
+    static constexpr bool EDGE_TOLERANT = false;
     static __device__ __forceinline__ Cell stone() { return {ONES, ONES, ONES}; }
     static __device__ __forceinline__ Cell pack(const uint32_t (&w)[8]) { return pack3(w); }
     static __device__ __forceinline__ void unpack(Cell c, uint32_t (&w)[8]) { unpack3(c, w); }
@@ -119,6 +121,16 @@ __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(p));
 }
+// same with an L2 eviction priority: ".L2::evict_last" for rows a second warp of the CTA reads again shortly (the pair two
+// neighbouring bands of the four-step kernel share), ".L2::evict_first" for rows nobody reads again
+#define FS3D_LD256_PRIO(NAME, PRIO)                                                                                  \
+    __device__ __forceinline__ void NAME(const uint8_t *p, uint32_t (&r)[8]) {                                       \
+        asm volatile("ld.global.nc.L1::no_allocate" PRIO ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                  \
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+                     : "l"(p));                                                                                      \
+    }
+FS3D_LD256_PRIO(ld256_keep, ".L2::evict_last")
+FS3D_LD256_PRIO(ld256_once, ".L2::evict_first")
 // same, through the coherent path: ghost planes are written by a peer GPU while this kernel runs.
 // (asm volatile statements keep their program order, so these stay behind the acquire of the arrival flag.)
 __device__ __forceinline__ void ld256_coherent(const uint8_t *p, uint32_t (&r)[8]) {
@@ -440,20 +452,21 @@ __global__ void __launch_bounds__(THREADS, FS3D_MINB) step_kernel(const StepPara
 #else
         constexpr bool PAIR1 = !R::COLUMN_FORM || NS == 1 || XW == 2 || SKIP == 1;
 #endif
-        // One-way message between the two warps of a pair (XW = 2): a tagged 32-bit mailbox in shared memory.
-        // Both warps count messages alike; messages alternate direction (pre: half 1 -> 0, post: half 0 -> 1),
-        // so message k + 2 reuses the slot of message k only after its reader has answered message k + 1.
+        // One-way message between the two warps of a pair (XW = 2): a tagged 32-bit mailbox in shared memory (tag in
+        // bits 28-31, 28 payload bits).  Both warps count messages alike; messages alternate direction (pre: half
+        // 1 -> 0, post: half 0 -> 1), so message k + 2 reuses the slot of message k only after its reader has
+        // answered message k + 1.
         auto xmail = [&](uint32_t from_half, uint32_t from_lane, uint32_t payload) -> uint32_t {
             ++xseq;
-            const uint32_t tag = (xseq & 0x3FFFu) << 18;
+            const uint32_t tag = xseq << 28;              // strict alternation: four tag bits are plenty
             volatile uint32_t *slot = xch + (xseq & 1u);
             if (half == from_half) {
-                if (lane == from_lane) *slot = tag | payload;
+                if (lane == from_lane) *slot = (payload & 0x0FFFFFFFu) | tag;
                 return 0u;
             }
             uint32_t v;
-            do { v = *slot; } while ((v & 0xFFFC0000u) != tag);
-            return v & 0x3FFFFu;
+            do { v = *slot; } while ((v & 0xF0000000u) != tag);
+            return R::EDGE_TOLERANT ? v : (v & 0x0FFFFFFFu);
         };
         // XY sub-step on (upper, lower) of both rows at once, every block evaluated once (bitslice.cuh,
         // xy_pair_substep*); the upper row is plane yu

@@ -19,11 +19,14 @@ static int bitpos(int x) { return 8 * (x & 3) + ((x >> 2) & 7); }
 enum { E = 0, S = 1, W = 2, X = 3 };
 static int dens(int m) { return m == S ? 2 : (m == W ? 1 : 0); }
 static int heav(int u, int l) { if (u != S && u != W) return 0; if (l != E && l != W) return 0; return dens(u) > dens(l); }
-static void rule(int &a, int &b, int &c, int &d, int coin) {
-    if (heav(a, c)) std::swap(a, c);
-    if (heav(b, d)) std::swap(b, d);
-    if (heav(a, d) && b != X) std::swap(a, d); else if (heav(b, c) && a != X) std::swap(b, c);
-    if (coin) { if ((a == W && b == E) || (b == W && a == E)) std::swap(a, b); }
+// returns whether the block is enabled: something fell or slid, or a lateral move is possible whatever the coin says
+static int rule(int &a, int &b, int &c, int &d, int coin) {
+    int en = 0;
+    if (heav(a, c)) { std::swap(a, c); en = 1; }
+    if (heav(b, d)) { std::swap(b, d); en = 1; }
+    if (heav(a, d) && b != X) { std::swap(a, d); en = 1; } else if (heav(b, c) && a != X) { std::swap(b, c); en = 1; }
+    if ((a == W && b == E) || (b == W && a == E)) { en = 1; if (coin) std::swap(a, b); }
+    return en;
 }
 
 static int unit_tests() {
@@ -56,9 +59,9 @@ static int unit_tests() {
             C.p0 |= (c[i] & 1u) << i; C.p1 |= ((c[i] >> 1) & 1u) << i; D.p0 |= (d[i] & 1u) << i; D.p1 |= ((d[i] >> 1) & 1u) << i;
             R |= (uint32_t)r[i] << i;
         }
-        block_rule(A, B, C, D, R);
+        const uint32_t EN = block_rule(A, B, C, D, R);
         for (int i = 0; i < 32; ++i) {
-            rule(a[i], b[i], c[i], d[i], r[i]);
+            if (rule(a[i], b[i], c[i], d[i], r[i]) != (int)((EN >> i) & 1u)) bad++;
             int ga = ((A.p0 >> i) & 1) | (((A.p1 >> i) & 1) << 1), gb = ((B.p0 >> i) & 1) | (((B.p1 >> i) & 1) << 1);
             int gc = ((C.p0 >> i) & 1) | (((C.p1 >> i) & 1) << 1), gd = ((D.p0 >> i) & 1) | (((D.p1 >> i) & 1) << 1);
             if (ga != a[i] || gb != b[i] || gc != c[i] || gd != d[i]) bad++;
@@ -96,6 +99,9 @@ static void emu_xy(Grid &g, uint32_t key, int oy) {
         }
 }
 // the same sub-step through the pair functions (every block evaluated once, rows taken two at a time)
+// the exchanged edge words are E-packed (bitslice.cuh): every bit outside 0x03030303 is "don't care" — the kernels
+// put the mailbox tag there — so the emulation sets them all
+static const uint32_t GARBAGE = ~NB_STONE2;
 template <int OX>
 static void emu_xy_pair(Grid &g, uint32_t key, int oy) {
     for (int z = 0; z < g.nz; z += 2)
@@ -110,12 +116,12 @@ static void emu_xy_pair(Grid &g, uint32_t key, int oy) {
             }
             for (int xw = 0; xw < W; ++xw) {
                 if (OX == 0) xy_pair_substep0(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw]);
-                else xy_pair_substep1(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw], xw + 1 < W ? first[xw + 1] : 0xFFu, carry[xw]);
+                else xy_pair_substep1(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw], xw + 1 < W ? (first[xw + 1] | GARBAGE) : NB_STONE2, carry[xw]);
             }
             if (OX == 1)
                 for (int xw = 0; xw < W; ++xw) {
                     uint32_t en = 0;
-                    xy_pair_post1(U0[xw], L0[xw], U1[xw], L1[xw], xw > 0 ? carry[xw - 1] : xy_wall_first(first[0], en));
+                    xy_pair_post1(U0[xw], L0[xw], U1[xw], L1[xw], xw > 0 ? (carry[xw - 1] | GARBAGE) : xy_wall_first(first[0] | GARBAGE, en));
                 }
             for (int xw = 0; xw < W; ++xw) {
                 wrw(g, z, y0 + 1, xw, U0[xw]); wrw(g, z, y0, xw, L0[xw]); wrw(g, z + 1, y0 + 1, xw, U1[xw]); wrw(g, z + 1, y0, xw, L1[xw]);

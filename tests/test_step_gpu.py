@@ -373,6 +373,18 @@ def test_four_step_passes_with_many_bands_and_segments(fs3d, oracle):
     run_and_compare(fs3d, oracle, 1024, 520, 13, scene=3, seed=5, steps=12, every=12)
 
 
+@pytest.mark.parametrize("dims", [(2048, 160, 50), (2048, 64, 130), (1024, 520, 13), (1024, 96, 120)])
+def test_four_step_passes_with_grouped_bands(fs3d, oracle, dims, monkeypatch):
+    # big single slabs give every CTA a span of (group of neighbouring bands x iteration) and stagger its units one
+    # y-block each; FS3D_S4_GROUP_SPAN=1 forces that split onto grids the oracle finishes in seconds:
+    # partial last groups, spans across group boundaries, units whose shifted segment is empty
+    monkeypatch.setenv("FS3D_S4_GROUP_SPAN", "1")
+    nx, ny, nz = dims
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=4, seed=11, steps=12, every=4)
+    monkeypatch.setenv("FS3D_S4_GROUP_SPAN", "0")       # never grouped: same result
+    run_and_compare(fs3d, oracle, nx, ny, nz, scene=4, seed=11, steps=8, every=8)
+
+
 def test_four_two_and_one_step_passes_agree(fs3d):
     for n in (1024, 2048):
         digs = {}

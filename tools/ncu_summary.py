@@ -56,7 +56,7 @@ def main():
                      "(mean over the captured launches: both x-offsets, and both step parities for the single-step "
                      "kernels). 2048 = 2048^3 grid, 17.18 GB algorithmic per single-step launch; a fused launch "
                      "advances two steps (34.36 GB algorithmic by the 2 B/update definition) on the same traffic; a fused4 launch (step4_kernel) "
-                     "advances FOUR steps and reads 7/6 of the grid (the first z-pair of every band of six is loaded twice). "
+                     "advances FOUR steps; the first z-pair of every band of four is loaded twice (5/4 of the grid), but on big single slabs the second load hits L2 (grouped bands, staggered units: 25/24 from DRAM). "
                      "4096x4096x512 = one rank's slab of 4096^3 on 8 GPUs (warp-pair kernels), same voxel count"}
     with open(tp, "w") as f:
         json.dump(out, f, indent=1)
