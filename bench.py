@@ -587,8 +587,8 @@ def ours(args):
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-            # the dominant kernel of the N = 1 run: the four-step kernel where fs3d_step uses it (rows of 1024 / 2048 voxels)
-            traffic = (tj.get(f"{n}_fused4") if n in (1024, 2048) else tj.get(f"{n}_fused")) if world_size == 1 else None
+            # the dominant kernel of the N = 1 run: the four-step kernel where fs3d_step uses it (rows of 1024 / 2048 / 4096 voxels)
+            traffic = (tj.get(f"{n}_fused4") if n in (1024, 2048, 4096) else tj.get(f"{n}_fused")) if world_size == 1 else None
 
     line = {
         "metric": METRIC, "value": value, "unit": "voxel-updates/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
@@ -612,7 +612,7 @@ def ours(args):
                      "dram_gbs_from_traffic": (traffic * launches / (ms * 1e-3) / 1e9) if (traffic and world_size == 1) else None,
                      "hardware_frac": (traffic * launches / (ms * 1e-3) / 1e9 / hbm_peak) if (traffic and world_size == 1) else None,
                      "algorithmic_bytes_per_voxel_update": 2,
-                     "kernel": ("fs3d::step4_kernel (four steps per launch)" if (world_size == 1 and n in (1024, 2048) and launches * 4 <= K + 3)
+                     "kernel": ("fs3d::step4_kernel (four steps per launch)" if (world_size == 1 and n in (1024, 2048, 4096) and launches * 4 <= K + 3)
                                 else "fs3d::step_kernel<NS=2> (two steps per launch)"),
                      "note": "achieved = 2 B x voxel-updates per launch / duration, per GPU. One launch advances every "
                              "voxel several steps while moving ~2 B per voxel, so frac can exceed 1: the real DRAM bytes "

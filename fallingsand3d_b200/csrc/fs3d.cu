@@ -520,7 +520,7 @@ static int exchange_halos(fs3d_world *w) {
 // internal boundaries lie on even planes (stage A then needs no halo at all) with at least four planes each.
 static bool slab_fuse4_capable(const fs3d_world *w, const Slab &s) {
     if (w->version != 1 || (w->desc.flags & (FS3D_FLAG_NO_FUSE | FS3D_FLAG_NO_FUSE4 | FS3D_FLAG_SKIP_SETTLED))) return false;
-    if (w->desc.nx != 1024 && w->desc.nx != 2048) return false;
+    if (w->desc.nx != 1024 && w->desc.nx != 2048 && w->desc.nx != 4096) return false;
     if (s.nzl < 2 || w->desc.ny < 2) return false;
     const bool has_lo = s.z0 > 0, has_hi = s.z0 + s.nzl < w->desc.nz;
     if ((has_lo || has_hi) && ((s.z0 & 1u) || s.nzl < 4)) return false;

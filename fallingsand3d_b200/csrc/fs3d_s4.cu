@@ -19,11 +19,13 @@ static cudaError_t launch_one(const Step4Params &p, unsigned grid, cudaStream_t 
     return cudaGetLastError();
 }
 
-// xw = warps per band (1: nx = 1024, 2: nx = 2048); grid = CTAs (one per SM: the kernel parks 210 KB of pipeline state in shared memory);
+// xw = warps per band (1: nx = 1024, 2: nx = 2048, 4: nx = 4096); grid = CTAs (one per SM: the kernel parks 210 KB of pipeline state in shared memory);
 // nbr = the slab has z-neighbours (coherent loads, bounded waits on the arrival counters)
 cudaError_t step4_launch(int xw, int nbr, const Step4Params &p, unsigned grid, cudaStream_t stream) {
     if (xw == 1) return nbr ? launch_one<1, 1>(p, grid, stream) : launch_one<1, 0>(p, grid, stream);
-    return nbr ? launch_one<2, 1>(p, grid, stream) : launch_one<2, 0>(p, grid, stream);
+    if (xw == 2) return nbr ? launch_one<2, 1>(p, grid, stream) : launch_one<2, 0>(p, grid, stream);
+    if (xw == 4) return nbr ? launch_one<4, 1>(p, grid, stream) : launch_one<4, 0>(p, grid, stream);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t halo4_launch(const Halo4Params &h, cudaStream_t stream) {

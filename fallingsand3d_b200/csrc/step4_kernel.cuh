@@ -12,15 +12,16 @@
 // — and parks each pair's pipeline state (the carried planes of both stages: 28 words per lane) in shared memory until
 // the next y-block.  The first A-pair of a band is recomputed by the band below ((P+1)/P of the loads and of stage A);
 // everything else is done once.  DRAM sees every byte read (P+1)/P times and written once per FOUR steps.
-// Rows of 2048 voxels use two warps per band (XW = 2), which exchange the word-boundary cells of stage B's odd
-// x-offset through the tagged mailboxes of step_kernel.cuh.
+// Rows of 2048 / 4096 voxels use two / four warps per band (XW = 2, 4); neighbouring warps exchange the word-boundary
+// cells of stage B's odd x-offset through the tagged mailboxes of step_kernel.cuh.
 //
-// Used by fs3d_step for worlds of schedule version 1 without skipping whose rows are 1024 or 2048 voxels wide, when four
+// Used by fs3d_step for worlds of schedule version 1 without skipping whose rows are 1024, 2048 or 4096 voxels wide, when four
 // steps remain and the step index is a multiple of four: single slabs, and z-slabs with fused-push neighbours (NBR = 1:
 // two ghost planes per side, delivered by halo4_kernel after the pass).  Everything else keeps the two-step pass.  Results are identical by construction
 // and tested against the oracle (every parity test with nx in {1024, 2048}, the full 2048^3 compare, bench digests).
 // No reference counterpart; call site: /root/reference/src/engine/engine.cpp:59-70.
 #pragma once
+#include <type_traits>
 #include "step_kernel.cuh"
 
 namespace fs3d {
@@ -108,18 +109,21 @@ template <int XW, int NBR, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) {
     using R = Rules1;
     using Cell = P2;
-    static_assert(XW == 1 || XW == 2, "one warp per 1024 voxels of a row");
-    constexpr bool XCH = XW == 2;
+    static_assert(XW == 1 || XW == 2 || XW == 4, "one warp per 1024 voxels of a row");
+    static_assert((THREADS / 32) % XW == 0, "whole bands per CTA");
+    constexpr bool XCH = XW > 1;
     constexpr uint32_t UNITS = THREADS / 32 / XW;           // bands marched side by side in a CTA
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t wic = threadIdx.x >> 5;
     const uint32_t pic = wic / XW, half = wic % XW;
     const uint32_t gw = blockIdx.x * UNITS + pic, nw = gridDim.x * UNITS;
-    __shared__ uint32_t xch_smem[XCH ? UNITS * 4 : 1];
-    volatile uint32_t *const xch = xch_smem + (XCH ? pic * 4 : 0);
+    // one mailbox (two slots) per boundary between neighbouring warps of a band
+    constexpr uint32_t NBOX = XCH ? (XW - 1) * 2 : 1;
+    __shared__ uint32_t xch_smem[XCH ? UNITS * NBOX : 1];
+    volatile uint32_t *const xch = xch_smem + (XCH ? pic * NBOX : 0);
     uint32_t xseq = 0;
     if (XCH) {
-        if (threadIdx.x < UNITS * 4) xch_smem[threadIdx.x] = 0u;
+        if (threadIdx.x < UNITS * NBOX) xch_smem[threadIdx.x] = 0u;
         __syncthreads();
     }
     extern __shared__ __align__(16) uint32_t s4_smem[];
@@ -158,17 +162,24 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
         hi0 = per * (blockIdx.x + 1u) < totalg ? per * (blockIdx.x + 1u) : totalg;
     }
 
-    // one-way message between the two warps of a unit (see step_kernel.cuh)
-    auto xmail = [&](uint32_t from_half, uint32_t from_lane, uint32_t payload) -> uint32_t {
+    // Messages between neighbouring warps of a band (the tagged mailboxes of step_kernel.cuh, one per warp boundary).
+    // xmail<0>: every warp hands `payload` of its lane 0 DOWN to the warp on its left and returns what the warp on its
+    // right sent (undefined for the last warp); xmail<1>: lane 31's payload goes UP to the right, the left one's comes
+    // back (undefined for the first warp).  On every boundary the two directions alternate strictly, so message k + 2
+    // reuses the slot of message k only after its reader has answered message k + 1; four tag bits are plenty.
+    auto xmail = [&](auto dir, uint32_t payload) -> uint32_t {
+        constexpr uint32_t UP = decltype(dir)::value;
         ++xseq;
         const uint32_t tag = xseq << 28;
-        volatile uint32_t *slot = xch + (xseq & 1u);
-        if (half == from_half) {
-            if (lane == from_lane) *slot = (payload & 0x0FFFFFFFu) | tag;
-            return 0u;
+        const uint32_t s = xseq & 1u;
+        const bool sends = UP ? half + 1u < (uint32_t)XW : half > 0u, receives = UP ? half > 0u : half + 1u < (uint32_t)XW;
+        // boundary b lies between warps b and b + 1
+        if (sends && lane == (UP ? 31u : 0u)) xch[(UP ? half : half - 1u) * 2u + s] = (payload & 0x0FFFFFFFu) | tag;
+        uint32_t v = 0u;
+        if (receives) {
+            volatile uint32_t *slot = xch + (UP ? half - 1u : half) * 2u + s;
+            do { v = *slot; } while ((v & 0xF0000000u) != tag);
         }
-        uint32_t v;
-        do { v = *slot; } while ((v & 0xF0000000u) != tag);
         return v;                                         // Rules1's edge bits tolerate the tag (bitslice.cuh, E-packing)
     };
     // XY sub-step on (upper, lower) of both rows; x-offset 0 (stage A) or 1 (stage B, cells of the word-straddling block
@@ -180,14 +191,14 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
         const uint32_t r0 = hash_word(key + hxy[0] + yu * HC2), r1 = hash_word(key + hxy[1] + yu * HC2);
         const uint32_t first = R::first_bits(up[0], lw[0], up[1], lw[1]);
         uint32_t xin = R::NB_STONE;
-        if (XCH) xin = xmail(1u, 0u, first);
+        if (XCH) xin = xmail(std::integral_constant<uint32_t, 0u>{}, first);
         uint32_t b = __shfl_down_sync(ONES, first, 1);
-        if (XCH && half == 0u && lane == 31u) b = xin;
+        if (XCH && half + 1u < (uint32_t)XW && lane == 31u) b = xin;
         uint32_t carry;
         R::xy1(up[0], lw[0], up[1], lw[1], r0, r1, hasn ? b : R::NB_STONE, carry);
-        if (XCH) xin = xmail(0u, 31u, carry);
+        if (XCH) xin = xmail(std::integral_constant<uint32_t, 1u>{}, carry);
         uint32_t a = __shfl_up_sync(ONES, carry, 1);
-        if (XCH && half == 1u && lane == 0u) a = xin;
+        if (XCH && half > 0u && lane == 0u) a = xin;
         uint32_t enw = 0;
         const uint32_t wall = R::wall_first(first, enw);
         if (!hasp) a = wall;

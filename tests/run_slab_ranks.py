@@ -24,11 +24,13 @@ def main():
     cases = [(64, 24, 18, 3, 12, True, 0), (64, 24, 18, 3, 12, False, 0), (2048, 32, 24, 4, 10, True, 0),
              (2048, 32, 24, 4, 10, False, 0), (256, 256, 256, 2, 40, True, 0), (4096, 16, 20, 3, 6, True, 0),
              (1024, 48, 40, 4, 16, True, 0), (2048, 64, 32, 4, 12, True, 0),      # four-step passes across ranks (slab.fuse4)
+             (4096, 24, 32, 4, 12, True, 0),
              (64, 96, 48, 1, 60, True, SK), (64, 96, 48, 1, 30, False, SK), (4096, 70, 16, 4, 12, True, SK)]
     for (nx, ny, nz, scene, steps, p2p, flags) in cases:
         sw = SlabWorld(nx, ny, nz, seed=5, p2p=p2p, flags=flags)
         assert sw.p2p == p2p
-        if p2p and nx in (1024, 2048) and not flags and nz // dist.get_world_size() >= 4:
+        nzl = nz // dist.get_world_size()
+        if p2p and nx in (1024, 2048, 4096) and not flags and nz % dist.get_world_size() == 0 and nzl >= 4 and nzl % 2 == 0:
             assert sw.fuse4, "every rank's slab supports four-step passes here"
         sw.generate(scene, 3)
         ref = None

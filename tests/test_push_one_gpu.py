@@ -172,7 +172,7 @@ def test_push_watchdog_names_the_stalled_neighbour(fs3d, monkeypatch):
 
 # ---- four steps per pass across slabs: two ghost planes per side, delivered by halo4_kernel after every pass ----
 @pytest.mark.parametrize("nslabs,dims,scene", [(2, (1024, 16, 12), 3), (3, (2048, 40, 26), 4), (4, (2048, 24, 16), 4), (3, (1024, 70, 30), 4),
-                                               (2, (2048, 9, 9), 3)])
+                                               (2, (2048, 9, 9), 3), (3, (4096, 20, 26), 4), (2, (4096, 33, 12), 3)])
 def test_inprocess_world_four_step_passes_on_one_device(fs3d, oracle, nslabs, dims, scene):
     nx, ny, nz = dims
     g = oracle.generate(nx, ny, nz, scene, 5)
@@ -196,7 +196,7 @@ def test_inprocess_world_four_step_passes_on_one_device(fs3d, oracle, nslabs, di
         assert w.step_timed(8)[1] == 2 * 2 * 4          # afterwards kernel + delivery
 
 
-@pytest.mark.parametrize("k,dims,scene", [(2, (1024, 32, 20), 4), (3, (2048, 48, 26), 4), (3, (1024, 9, 14), 3)])
+@pytest.mark.parametrize("k,dims,scene", [(2, (1024, 32, 20), 4), (3, (2048, 48, 26), 4), (3, (1024, 9, 14), 3), (2, (4096, 24, 20), 4)])
 def test_attached_slab_worlds_four_step_passes(fs3d, oracle, k, dims, scene):
     nx, ny, nz = dims
     g = oracle.generate(nx, ny, nz, scene, 3)

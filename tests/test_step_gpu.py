@@ -357,9 +357,10 @@ def test_step_host_packed_streams_a_packed_host_grid(fs3d, oracle, dims, m8):
             w.step_host_packed(host, out, 3)
 
 
-# ---- four steps per pass (step4_kernel.cuh): rows of 1024 / 2048 voxels, step index a multiple of four ----
+# ---- four steps per pass (step4_kernel.cuh): rows of 1024 / 2048 / 4096 voxels (one, two, four warps per band), step index
+# a multiple of four ----
 @pytest.mark.parametrize("dims", [(1024, 6, 5), (2048, 6, 4), (1024, 1, 2), (2048, 2, 2), (1024, 9, 3), (2048, 40, 31), (1024, 70, 26),
-                                  (2048, 33, 12), (1024, 300, 4)])
+                                  (2048, 33, 12), (1024, 300, 4), (4096, 6, 4), (4096, 2, 2), (4096, 37, 21), (4096, 120, 9)])
 @pytest.mark.parametrize("every", [4, 8, 5, 13])
 def test_four_step_passes_match_oracle(fs3d, oracle, dims, every):
     # every = 4, 8: nothing but four-step passes; 5, 13: four-step passes mixed with two-step and single passes
@@ -373,7 +374,7 @@ def test_four_step_passes_with_many_bands_and_segments(fs3d, oracle):
     run_and_compare(fs3d, oracle, 1024, 520, 13, scene=3, seed=5, steps=12, every=12)
 
 
-@pytest.mark.parametrize("dims", [(2048, 160, 50), (2048, 64, 130), (1024, 520, 13), (1024, 96, 120)])
+@pytest.mark.parametrize("dims", [(2048, 160, 50), (2048, 64, 130), (1024, 520, 13), (1024, 96, 120), (4096, 48, 66)])
 def test_four_step_passes_with_grouped_bands(fs3d, oracle, dims, monkeypatch):
     # big single slabs give every CTA a span of (group of neighbouring bands x iteration) and stagger its units one
     # y-block each; FS3D_S4_GROUP_SPAN=1 forces that split onto grids the oracle finishes in seconds:
@@ -386,7 +387,7 @@ def test_four_step_passes_with_grouped_bands(fs3d, oracle, dims, monkeypatch):
 
 
 def test_four_two_and_one_step_passes_agree(fs3d):
-    for n in (1024, 2048):
+    for n in (1024, 2048, 4096):
         digs = {}
         for name, flags in (("four", 0), ("two", fs3d.FLAG_NO_FUSE4), ("one", fs3d.FLAG_NO_FUSE)):
             with fs3d.VoxelWorld(n, 256, 64, seed=5, flags=flags) as w:
