@@ -551,7 +551,8 @@ static int launch_halo4(fs3d_world *w, Slab &s, int b, int near) {
     return FS3D_OK;
 }
 
-static int launch_fused4(fs3d_world *w, Slab &s) {
+// band_lo / band_hi: the bands of this launch (fs3d_step_host streams the grid through in chunks of bands); default = all
+static int launch_fused4(fs3d_world *w, Slab &s, uint32_t band_lo = 0, uint32_t band_hi = ~0u) {
     Step4Params p{};
     p.src = s.buf[w->cur];
     p.dst = s.buf[w->cur ^ 1];
@@ -560,6 +561,9 @@ static int launch_fused4(fs3d_world *w, Slab &s) {
     p.nA = (s.nzl - 1) / 2 + 1;                 // pair_layout with lz_first = 1 (z0 is even)
     p.nB = s.nzl / 2 + 1;                       // pair_layout with lz_first = 0
     p.nbands = (p.nB + S4_P - 1) / S4_P;
+    band_hi = std::min(band_hi, p.nbands);
+    if (band_lo >= band_hi) return FS3D_OK;
+    p.band0 = band_lo; p.nbands = band_hi - band_lo;
     p.nit = w->desc.ny / 2 + 4;
     for (int i = 0; i < 4; ++i) {
         p.key_xy[i] = step_key(w->desc.seed, w->step + (uint64_t)i, 0);
@@ -1568,12 +1572,20 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
     }
     // A z-pair of planes is closed under a pass, so the grid streams through in chunks
     // of whole pairs: upload chunk k+1 | step chunk k | download chunk k-1 all overlap.
+    // n_steps = 4 (fuse4_ok worlds, step index a multiple of four): chunks of whole BANDS of the four-step kernel
+    // (step4_kernel.cuh).  Band b finishes local planes [8b, 8b + 8) and reads planes [8b - 1, 8b + 8], so a chunk's
+    // upload runs one plane ahead of its download: planes (8 b0, 8 b1] go up, planes [8 b0, 8 b1) come down.
     const int ns = (int)n_steps;
+    const bool four = ns == 4;
     const uint32_t hoff = (uint32_t)((w->step >> 1) & 1);
     const PairLayout L = pair_layout(s, hoff);
     const size_t pb = plane_bytes(w);
-    const uint32_t pairs_per_chunk = std::max<uint32_t>(1, (uint32_t)((FS3D_HOST_CHUNK_MIB << 20) / (2 * pb)));
-    const uint32_t nchunks = (L.npairs + pairs_per_chunk - 1) / pairs_per_chunk;
+    const uint32_t unit_planes = four ? 2u * S4_P : 2u;                        // planes per band / per z-pair
+    const uint32_t nunits = four ? (s.nzl / 2 + 1 + S4_P - 1) / S4_P : L.npairs;
+    uint64_t chunk_bytes = FS3D_HOST_CHUNK_MIB << 20;
+    if (const char *e = std::getenv("FS3D_HOST_CHUNK_BYTES")) chunk_bytes = std::max<uint64_t>(1, std::strtoull(e, nullptr, 10));   // tests: many small chunks
+    const uint32_t pairs_per_chunk = (uint32_t)std::min<uint64_t>(nunits ? nunits : 1, std::max<uint64_t>(1, chunk_bytes / (unit_planes * pb)));
+    const uint32_t nchunks = (nunits + pairs_per_chunk - 1) / pairs_per_chunk;
     while (s.ev_chunk.size() < 2 * (size_t)nchunks) {
         cudaEvent_t e;
         FS3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1581,7 +1593,7 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
     }
     const uint32_t div = w->version == 2 ? 2u : 4u;         // voxels per packed byte
     if (packed) {
-        const size_t need = (size_t)pairs_per_chunk * 2 * pb / div;
+        const size_t need = (size_t)pairs_per_chunk * unit_planes * pb / div;
         if (s.stage_bytes < need) {
             for (auto &p : s.d_stage) { if (p) cudaFree(p); p = nullptr; }
             s.stage_bytes = 0;
@@ -1598,19 +1610,23 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
     FS3D_CUDA(cudaStreamWaitEvent(s.s_h2d, s.ev_t0, 0));
     uint8_t *src = s.buf[w->cur], *dst = s.buf[w->cur ^ 1];
     for (uint32_t c = 0; c < nchunks; ++c) {
-        const uint32_t p0 = c * pairs_per_chunk, p1 = std::min(L.npairs, p0 + pairs_per_chunk);
-        // owned local planes covered by pairs [p0, p1): lz in [lo, hi)
-        uint32_t lo = L.lz_first + 2 * p0, hi = L.lz_first + 2 * p1;
+        const uint32_t p0 = c * pairs_per_chunk, p1 = std::min(nunits, p0 + pairs_per_chunk);
+        // owned local planes that go up before this chunk is stepped: lz in [lo, hi); that come down after it: [dlo, dhi)
+        uint32_t lo = four ? unit_planes * p0 + 1 : L.lz_first + 2 * p0, hi = four ? unit_planes * p1 + 1 : L.lz_first + 2 * p1;
         lo = std::max(lo, 1u); hi = std::min(hi, s.nzl + 1);
+        uint32_t dlo = lo, dhi = hi;
+        if (four) { dlo = std::max(unit_planes * p0, 1u); dhi = std::min(unit_planes * p1, s.nzl + 1); }
         const size_t off = pb * lo, bytes = pb * (size_t)(hi - lo);
-        const uint64_t n16 = bytes / 16;
+        const size_t doff = pb * dlo, dbytes = pb * (size_t)(dhi - dlo);
+        const uint64_t n16 = bytes / 16, dn16 = dbytes / 16;
         if (packed) {
             // upload the packed chunk into staging slot c & 1 (free once chunk c - 2 was unpacked), unpack it into place
             if (c >= 2) FS3D_CUDA(cudaStreamWaitEvent(s.s_h2d, s.ev_stage[c & 1], 0));
             FS3D_CUDA(cudaMemcpyAsync(s.d_stage[c & 1], host_in + pb / div * (size_t)(lo - 1), bytes / div, cudaMemcpyHostToDevice, s.s_h2d));
             FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
             FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
-            if (w->version == 2) unpack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint2 *>(s.d_stage[c & 1]), n16, src + off);
+            if (!n16) {}       // the last chunk of a four-step call may have nothing left to upload
+            else if (w->version == 2) unpack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint2 *>(s.d_stage[c & 1]), n16, src + off);
             else unpack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(reinterpret_cast<const uint32_t *>(s.d_stage[c & 1]), n16, src + off);
             FS3D_CUDA(cudaGetLastError());
             FS3D_CUDA(cudaEventRecord(s.ev_stage[c & 1], s.s_main));
@@ -1620,28 +1636,29 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
             FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c], s.s_h2d));
             FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_chunk[2 * c], 0));
         }
-        if (!packed || w->version == 2) {       // 2-bit codes cannot be out of range
+        if ((!packed || w->version == 2) && n16) {       // 2-bit codes cannot be out of range
             validate_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(src + off, n16, bad_bits(w), flag);
             FS3D_CUDA(cudaGetLastError());
             w->launches++;
         }
-        rc = launch_pairs(w, s, p0, p1, ns);
+        rc = four ? launch_fused4(w, s, p0, p1) : launch_pairs(w, s, p0, p1, ns);
         if (rc) { w->force_live = false; return rc; }
         if (packed) {
             // pack the stepped chunk into staging slot 2 + (c & 1) (free once chunk c - 2 was downloaded)
             if (c >= 2) FS3D_CUDA(cudaStreamWaitEvent(s.s_main, s.ev_stage[2 + (c & 1)], 0));
-            if (w->version == 2) pack4_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(dst + off, n16, reinterpret_cast<uint2 *>(s.d_stage[2 + (c & 1)]));
-            else pack2_kernel<<<grid_for(n16, s), 256, 0, s.s_main>>>(dst + off, n16, reinterpret_cast<uint32_t *>(s.d_stage[2 + (c & 1)]));
+            if (!dn16) {}
+            else if (w->version == 2) pack4_kernel<<<grid_for(dn16, s), 256, 0, s.s_main>>>(dst + doff, dn16, reinterpret_cast<uint2 *>(s.d_stage[2 + (c & 1)]));
+            else pack2_kernel<<<grid_for(dn16, s), 256, 0, s.s_main>>>(dst + doff, dn16, reinterpret_cast<uint32_t *>(s.d_stage[2 + (c & 1)]));
             FS3D_CUDA(cudaGetLastError());
             w->launches++;
         }
         FS3D_CUDA(cudaEventRecord(s.ev_chunk[2 * c + 1], s.s_main));
         FS3D_CUDA(cudaStreamWaitEvent(s.s_d2h, s.ev_chunk[2 * c + 1], 0));
         if (packed) {
-            FS3D_CUDA(cudaMemcpyAsync(host_out + pb / div * (size_t)(lo - 1), s.d_stage[2 + (c & 1)], bytes / div, cudaMemcpyDeviceToHost, s.s_d2h));
+            if (dbytes) FS3D_CUDA(cudaMemcpyAsync(host_out + pb / div * (size_t)(dlo - 1), s.d_stage[2 + (c & 1)], dbytes / div, cudaMemcpyDeviceToHost, s.s_d2h));
             FS3D_CUDA(cudaEventRecord(s.ev_stage[2 + (c & 1)], s.s_d2h));
-        } else {
-            FS3D_CUDA(cudaMemcpyAsync(host_out + pb * (size_t)(lo - 1), dst + off, bytes, cudaMemcpyDeviceToHost, s.s_d2h));
+        } else if (dbytes) {
+            FS3D_CUDA(cudaMemcpyAsync(host_out + pb * (size_t)(dlo - 1), dst + doff, dbytes, cudaMemcpyDeviceToHost, s.s_d2h));
         }
     }
     w->force_live = false;
@@ -1660,20 +1677,30 @@ static int step_host_stream(fs3d_world *w, const uint8_t *host_in, uint8_t *host
 
 int fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps) {
     if (!w || !host_in || !host_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
-    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host advances 1 or 2 steps per call");
+    if (n_steps != 1 && n_steps != 2 && n_steps != 4) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host advances 1, 2 or 4 steps per call");
     if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
+    if (n_steps == 4 && (w->step & 3)) return fail(FS3D_ERR_INVALID_ARG, "a 4-step pass must start on a step index that is a multiple of four");
     if (w->slabs.size() != 1 || (w->external && w->desc.nz != w->slabs[0].nzl))
         return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host needs a single-slab world that holds the whole grid "
                                           "(ranks use fs3d_slab_step_host_begin + fs3d_slab_step_host)");
+    if (n_steps == 4 && !fuse4_ok(w)) {        // no four-step kernel for this world: two streamed two-step passes
+        int rc = step_host_stream(w, host_in, host_out, 2);
+        return rc ? rc : step_host_stream(w, host_out, host_out, 2);
+    }
     return step_host_stream(w, host_in, host_out, n_steps);
 }
 
 int fs3d_step_host_packed(fs3d_world *w, const uint8_t *packed_in, uint8_t *packed_out, uint32_t n_steps) {
     if (!w || !packed_in || !packed_out) return fail(FS3D_ERR_INVALID_ARG, "NULL argument");
-    if (n_steps != 1 && n_steps != 2) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host_packed advances 1 or 2 steps per call");
+    if (n_steps != 1 && n_steps != 2 && n_steps != 4) return fail(FS3D_ERR_INVALID_ARG, "fs3d_step_host_packed advances 1, 2 or 4 steps per call");
     if (n_steps == 2 && (w->step & 1)) return fail(FS3D_ERR_INVALID_ARG, "a fused 2-step pass must start on an even step");
+    if (n_steps == 4 && (w->step & 3)) return fail(FS3D_ERR_INVALID_ARG, "a 4-step pass must start on a step index that is a multiple of four");
     if (w->slabs.size() != 1 || (w->external && w->desc.nz != w->slabs[0].nzl))
         return fail(FS3D_ERR_UNSUPPORTED, "fs3d_step_host_packed needs a single-slab world that holds the whole grid");
+    if (n_steps == 4 && !fuse4_ok(w)) {
+        int rc = step_host_stream(w, packed_in, packed_out, 2, true);
+        return rc ? rc : step_host_stream(w, packed_out, packed_out, 2, true);
+    }
     return step_host_stream(w, packed_in, packed_out, n_steps, true);
 }
 

@@ -51,7 +51,8 @@ struct Step4Params {
     uint32_t z0;                   // global z of local plane 1 (even)
     uint32_t nzl;                  // owned planes (local 1 .. nzl); local plane 0 / nzl+1 are the near ghosts
     uint32_t nA, nB;               // stage-A pairs a: local planes (1+2a, 2+2a); stage-B pairs q: local planes (2q, 2q+1)
-    uint32_t nbands;               // ceil(nB / S4_P)
+    uint32_t nbands;               // bands this launch marches: ceil(nB / S4_P), or a chunk of them (fs3d_step_host)
+    uint32_t band0;                // first band of this launch (single slabs only; 0 with neighbours)
     uint32_t nit;                  // march iterations: ny / 2 + 4
     uint32_t key_xy[4], key_zy[4]; // SCHEDULE.md §3 keys of steps t .. t+3
     // z-slabs (NBR = 1 instantiations): a neighbour holds the planes below / above.  Stage B's pair across a slab boundary
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) step4_kernel(const Step4Params p) 
             if (it_a >= it_b) continue;
         }
 
+        band += p.band0;
         const int qa = (int)(band * S4_P);
         const int nq = min(S4_P, (int)p.nB - qa);                 // B-pairs of this band; its A-pairs are a = qa-1 .. qa-1+nq
         if (NBR) {

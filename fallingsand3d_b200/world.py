@@ -161,7 +161,7 @@ class VoxelWorld:
         return ms.value, nl.value
 
     def step_host(self, grid_in, grid_out=None, n=1):
-        """Steps a host-resident grid n (1 or 2) steps: upload, kernels and download overlap chunk by chunk."""
+        """Steps a host-resident grid n (1, 2 or 4) steps: upload, kernels and download overlap chunk by chunk."""
         if grid_out is None:
             grid_out = grid_in
         for g in (grid_in, grid_out):

@@ -186,9 +186,12 @@ int  fs3d_kernel_launches(fs3d_world *w, uint64_t *out);   /* kernels this world
 int  fs3d_step_timed(fs3d_world *w, uint32_t n_steps, float *ms, uint64_t *kernel_launches);
 
 /* End-to-end step for a HOST-resident grid: equivalent to fs3d_upload(host_in); fs3d_step(n);
- * fs3d_download(host_out) with n = 1 or 2 (2 needs an even step index), but the grid streams
- * through the GPU in chunks of whole z-pairs so the H2D copy, the kernels and the D2H copy overlap
- * (use pinned host memory).  host_in may equal host_out.  Single-slab worlds only. */
+ * fs3d_download(host_out) with n = 1, 2 (needs an even step index) or 4 (a step index that is a
+ * multiple of four), but the grid streams through the GPU in chunks so the H2D copy, the kernels
+ * and the D2H copy overlap (use pinned host memory): chunks of whole z-pairs for n = 1, 2, of whole
+ * bands of the four-step kernel for n = 4 (worlds without one run two streamed 2-step passes).
+ * The call is bound by PCIe, so its cost barely depends on n: ask for as many steps as you need.
+ * host_in may equal host_out.  Single-slab worlds only. */
 int  fs3d_step_host(fs3d_world *w, const uint8_t *host_in, uint8_t *host_out, uint32_t n_steps);
 
 /* The same for a grid the host keeps PACKED in the checkpoint encoding (the payload of fs3d_save without its header:

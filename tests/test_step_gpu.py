@@ -210,6 +210,39 @@ def test_step_host_streams_a_host_grid(fs3d, oracle, dims):
             assert ei.value.code == -7
 
 
+@pytest.mark.parametrize("dims,packed", [((2048, 24, 20), False), ((1024, 40, 70), False), ((4096, 12, 34), False), ((2048, 16, 8), True),
+                                         ((1024, 300, 18), True), ((64, 40, 30), False), ((128, 24, 10), True)])
+def test_step_host_four_steps_per_call(fs3d, oracle, dims, packed, monkeypatch):
+    # n = 4: the grid streams through in chunks of whole bands of the four-step kernel, uploads one plane ahead of the
+    # downloads (tiny chunks here, so that every grid is cut into several); grids without that kernel (nx = 64, 128) take
+    # two streamed two-step passes
+    from fallingsand3d_b200 import checkpoint
+    nx, ny, nz = dims
+    monkeypatch.setenv("FS3D_HOST_CHUNK_BYTES", str(8 * nx * ny))      # one band (four z-pairs) per chunk
+    g = oracle.generate(nx, ny, nz, 4, 6)
+    enc = (lambda a: np.ascontiguousarray(checkpoint.pack2(a))) if packed else (lambda a: a.copy())
+    dec = (lambda a: checkpoint.unpack2(a, g.size).reshape(g.shape)) if packed else (lambda a: a)
+    host = enc(g)
+    out = np.empty_like(host)
+    with fs3d.VoxelWorld(nx, ny, nz, seed=11) as w:
+        call = w.step_host_packed if packed else w.step_host
+        t = 0
+        for n in (4, 4, 2, 1, 1, 4):
+            call(host, out, n)
+            oracle.run(g, 11, t, n)
+            t += n
+            assert np.array_equal(dec(out), g), f"after step {t}"
+            assert np.array_equal(w.download(), g)
+            assert w.step_index == t
+            host, out = out, host
+        call(host, host, 4)                              # in place
+        oracle.run(g, 11, t, 4)
+        assert np.array_equal(dec(host), g)
+        w.step(2)
+        with pytest.raises(fs3d.Fs3dError):              # step index 22: not a multiple of four
+            call(host, out, 4)
+
+
 def test_paint_sphere_brush(fs3d, oracle):
     import torch
     k = torch.cuda.device_count()
