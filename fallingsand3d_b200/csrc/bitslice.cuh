@@ -111,10 +111,26 @@ FS3D_HD void cswap(uint32_t m, P2 &x, P2 &y) {
     x.p0 ^= t0; y.p0 ^= t0; x.p1 ^= t1; y.p1 ^= t1;
 }
 
+// The block rule F, D, L in its plain mask-and-swap form: the specification block_rule() below is tested against
+// (tests/host/bitslice_host_test.cpp); the kernels do not call it.
+FS3D_HD uint32_t block_rule_plain(P2 &a, P2 &b, P2 &c, P2 &d, uint32_t r) {
+    uint32_t fa = heavier(a, c); cswap(fa, a, c);
+    uint32_t fb = heavier(b, d); cswap(fb, b, d);
+    uint32_t da = heavier(a, d) & ~(b.p0 & b.p1);
+    uint32_t db = heavier(b, c) & ~(a.p0 & a.p1);
+    cswap(da, a, d); cswap(db, b, c);
+    uint32_t la = ~a.p0 & a.p1 & ~b.p0 & ~b.p1;
+    uint32_t lb = ~b.p0 & b.p1 & ~a.p0 & ~a.p1;
+    uint32_t l = la | lb;
+    cswap(l & r, a, b);
+    return fa | fb | da | db | l;
+}
+
 // One three-input logic operation = one LOP3.  The block rule below is written as an explicit network of them (26 for
 // the whole rule; the compiler's own synthesis from the mask-and-swap formulation needs 39) and the step kernels are
-// bound by exactly this pipe.  FS3D_LOP3(name, expr) defines name(a, b, c) = expr: on the device a lop3.b32 whose
-// truth table is expr evaluated on the three selector constants, on the host the expression itself.
+// bound by exactly this pipe.  FS3D_LOP3(name, expr) defines name(a, b, c) = expr through its truth table (expr
+// evaluated at compile time on the three selector constants): on the device one lop3.b32 with that table, on the host
+// the same table applied minterm by minterm — so tests/host/ checks the very tables the kernels run.
 template <uint32_t LUT>
 FS3D_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)

@@ -11,14 +11,17 @@
 //     stage B (two more steps) on (the previous pair's upper row out of that buffer, this pair's lower row)  →  store
 // — and parks each pair's pipeline state (the carried planes of both stages: 28 words per lane) in shared memory until
 // the next y-block.  The first A-pair of a band is recomputed by the band below ((P+1)/P of the loads and of stage A);
-// everything else is done once.  DRAM sees every byte read (P+1)/P times and written once per FOUR steps.
+// everything else is done once.  DRAM sees every byte read (P+1)/P times and written once per FOUR steps — on big
+// single slabs 25/24 times: the units of a CTA then take neighbouring bands, staggered so that the shared pair's second
+// load hits L2 (`grp` below).
 // Rows of 2048 / 4096 voxels use two / four warps per band (XW = 2, 4); neighbouring warps exchange the word-boundary
 // cells of stage B's odd x-offset through the tagged mailboxes of step_kernel.cuh.
 //
 // Used by fs3d_step for worlds of schedule version 1 without skipping whose rows are 1024, 2048 or 4096 voxels wide, when four
 // steps remain and the step index is a multiple of four: single slabs, and z-slabs with fused-push neighbours (NBR = 1:
-// two ghost planes per side, delivered by halo4_kernel after the pass).  Everything else keeps the two-step pass.  Results are identical by construction
-// and tested against the oracle (every parity test with nx in {1024, 2048}, the full 2048^3 compare, bench digests).
+// two ghost planes per side, delivered by halo4_kernel after the pass), and by fs3d_step_host(…, 4) on chunks of bands.
+// Everything else keeps the two-step pass.  Results are identical by construction and tested against the oracle (every
+// parity test with nx in {1024, 2048, 4096}, the full 2048^3 compare, bench digests).
 // No reference counterpart; call site: /root/reference/src/engine/engine.cpp:59-70.
 #pragma once
 #include <type_traits>
@@ -29,7 +32,7 @@ namespace fs3d {
 // Band size P, y-block K and CTA size were chosen by A/B on a B200 (profiles/r02m_experiments_step4.txt): P = 4, K = 4
 // leaves 17.5 KB of parked state per warp, so TWELVE warps fit an SM (384-thread CTAs) instead of eight with P = 6,
 // K = 8 — 7 % faster at 2048^3 although 5/4 instead of 7/6 of stage A is recomputed (the kernel is ALU-bound and latency
-// hiding wins), the same at 1024^3.
+// hiding wins), the same at 1024^3.  Still the best shape after the ALU diet (profiles/r02p_experiments_alu.txt).
 #ifndef FS3D_S4_P
 #define FS3D_S4_P 4
 #endif

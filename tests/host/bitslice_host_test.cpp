@@ -59,6 +59,12 @@ static int unit_tests() {
             C.p0 |= (c[i] & 1u) << i; C.p1 |= ((c[i] >> 1) & 1u) << i; D.p0 |= (d[i] & 1u) << i; D.p1 |= ((d[i] >> 1) & 1u) << i;
             R |= (uint32_t)r[i] << i;
         }
+        {   // the LOP3 network against the plain mask-and-swap formulation, on all 32 bit positions at once
+            P2 A2 = A, B2 = B, C2 = C, D2 = D, A3 = A, B3 = B, C3 = C, D3 = D;
+            const uint32_t e2 = block_rule(A2, B2, C2, D2, R), e3 = block_rule_plain(A3, B3, C3, D3, R);
+            if (e2 != e3 || A2.p0 != A3.p0 || A2.p1 != A3.p1 || B2.p0 != B3.p0 || B2.p1 != B3.p1 || C2.p0 != C3.p0 || C2.p1 != C3.p1 ||
+                D2.p0 != D3.p0 || D2.p1 != D3.p1) bad++;
+        }
         const uint32_t EN = block_rule(A, B, C, D, R);
         for (int i = 0; i < 32; ++i) {
             if (rule(a[i], b[i], c[i], d[i], r[i]) != (int)((EN >> i) & 1u)) bad++;
