@@ -625,8 +625,9 @@ def ours(args):
                                 else "fs3d::step_kernel<NS=2> (two steps per launch)"),
                      "note": "achieved = 2 B x voxel-updates per launch / duration, per GPU. One launch advances every "
                              "voxel several steps while moving ~2 B per voxel, so frac can exceed 1: the real DRAM bytes "
-                             "are `traffic` (hardware_frac = traffic / time / peak); the four-step kernel is bound by the integer "
-                             "ALU pipe, not by HBM; `single_step` is the unfused kernel the 2 B/update roofline describes (0.96)"},
+                             "are `traffic` (hardware_frac = traffic / time / peak); the four-step kernel runs at ~0.8 of both of its "
+                             "roofs (DRAM traffic and the integer ALU pipe, ncu: profiles/r02s_*); `single_step` is the unfused "
+                             "kernel the 2 B/update roofline describes (0.96)"},
         "single_step": single,
         "two_steps_per_pass": two if world_size == 1 else None,
         "halo_wait": halo_wait if world_size > 1 else None,
