@@ -84,8 +84,10 @@ FS3D_HD uint32_t block_rule3(P3 &a, P3 &b, P3 &c, P3 &d, uint32_t r, uint32_t r2
 }
 
 // ---- XY sub-step on both rows of a z-pair, every block evaluated once (see bitslice.cuh for the geometry) ----------
-// Packed edge bits of the pair form: slot s = 0..5 for (U.p0, U.p1, U.p2, L.p0, L.p1, L.p2), bit 2s + row.  0xFFF = STONE.
-constexpr uint32_t NB_STONE3 = 0xFFFu;
+// Edge bits of the pair form, byte-packed like bitslice.cuh's E-packing with two more bits per row for the third plane:
+//   planes 0, 1: bit 8·(2p + row) + j;   plane 2: bit 8·row + 2 + j;   j = 0 for the block's upper plane (U), 1 for L.
+// Every other bit is "don't care" for the consumers (the warp-pair mailbox keeps its tag in bits 28-31).
+constexpr uint32_t NB_STONE3 = 0x03030F0Fu;
 
 FS3D_HD uint32_t xy3_pair_substep0(P3 &U0, P3 &L0, P3 &U1, P3 &L1, uint32_t rw0, uint32_t rw1) {
     P3 a{prmt(U0.p0, U1.p0, 0x6240), prmt(U0.p1, U1.p1, 0x6240), prmt(U0.p2, U1.p2, 0x6240)};
@@ -103,41 +105,52 @@ FS3D_HD uint32_t xy3_pair_substep0(P3 &U0, P3 &L0, P3 &U1, P3 &L1, uint32_t rw0,
     return en;
 }
 FS3D_HD uint32_t xy3_first_bits(P3 U0, P3 L0, P3 U1, P3 L1) {
-    return (U0.p0 & 1u) | ((U1.p0 & 1u) << 1) | ((U0.p1 & 1u) << 2) | ((U1.p1 & 1u) << 3) | ((U0.p2 & 1u) << 4) | ((U1.p2 & 1u) << 5) |
-           ((L0.p0 & 1u) << 6) | ((L1.p0 & 1u) << 7) | ((L0.p1 & 1u) << 8) | ((L1.p1 & 1u) << 9) | ((L0.p2 & 1u) << 10) | ((L1.p2 & 1u) << 11);
+    // byte 0 of the twelve plane words, gathered: [U0.p0, U1.p0, U0.p1, U1.p1], the same of L, [U0.p2, U1.p2, L0.p2, L1.p2]
+    const uint32_t fu = prmt(xy_gather1(U0.p0, U1.p0), xy_gather1(U0.p1, U1.p1), 0x7632);
+    const uint32_t fl = prmt(xy_gather1(L0.p0, L1.p0), xy_gather1(L0.p1, L1.p1), 0x7632);
+    const uint32_t f2 = prmt(xy_gather1(U0.p2, U1.p2), xy_gather1(L0.p2, L1.p2), 0x7632);
+    const uint32_t t01 = (fu & 0x01010101u) | (shl_add<1>(fl, 0u) & ~0x01010101u);
+    const uint32_t t2 = (shl_add<2>(f2, 0u) & 0x0404u) | (shr<13>(f2) & ~0x0404u);       // U: bits 0, 8 -> 2, 10; L: bits 16, 24 -> 3, 11
+    return (t01 & 0x03030303u) | (t2 & ~0x03030303u);
 }
-FS3D_HD uint32_t xy3_carry_bits(uint32_t w) { return ((w >> 23) & 1u) | ((w >> 30) & 2u); }   // bit 7 of bytes 2 (row 0) and 3 (row 1)
 FS3D_HD uint32_t xy3_pair_substep1(P3 &U0, P3 &L0, P3 &U1, P3 &L1, uint32_t rw0, uint32_t rw1, uint32_t nb, uint32_t &carry) {
     P3 a{prmt(U0.p0, U1.p0, 0x7351), prmt(U0.p1, U1.p1, 0x7351), prmt(U0.p2, U1.p2, 0x7351)};
     P3 c{prmt(L0.p0, L1.p0, 0x7351), prmt(L0.p1, L1.p1, 0x7351), prmt(L0.p2, L1.p2, 0x7351)};
-    P3 b{xy_right1(U0.p0, U1.p0, nb), xy_right1(U0.p1, U1.p1, nb >> 2), xy_right1(U0.p2, U1.p2, nb >> 4)};
-    P3 d{xy_right1(L0.p0, L1.p0, nb >> 6), xy_right1(L0.p1, L1.p1, nb >> 8), xy_right1(L0.p2, L1.p2, nb >> 10)};
+    const uint32_t nl = shr<1>(nb);
+    P3 b{xy_right1<0>(U0.p0, U1.p0, nb), xy_right1<1>(U0.p1, U1.p1, nb), xy_right1<0>(U0.p2, U1.p2, shr<2>(nb))};
+    P3 d{xy_right1<0>(L0.p0, L1.p0, nl), xy_right1<1>(L0.p1, L1.p1, nl), xy_right1<0>(L0.p2, L1.p2, shr<3>(nb))};
     const uint32_t en = block_rule3(a, b, c, d, prmt(rw0, rw1, 0x7351), prmt(coin2_word(rw0), coin2_word(rw1), 0x7351));
-    carry = xy3_carry_bits(b.p0) | (xy3_carry_bits(b.p1) << 2) | (xy3_carry_bits(b.p2) << 4) |
-            (xy3_carry_bits(d.p0) << 6) | (xy3_carry_bits(d.p1) << 8) | (xy3_carry_bits(d.p2) << 10);
-    U0.p0 = xy_merge1(a.p0, b.p0, 0); U1.p0 = xy_merge1(a.p0, b.p0, 1);
-    U0.p1 = xy_merge1(a.p1, b.p1, 0); U1.p1 = xy_merge1(a.p1, b.p1, 1);
-    U0.p2 = xy_merge1(a.p2, b.p2, 0); U1.p2 = xy_merge1(a.p2, b.p2, 1);
-    L0.p0 = xy_merge1(c.p0, d.p0, 0); L1.p0 = xy_merge1(c.p0, d.p0, 1);
-    L0.p1 = xy_merge1(c.p1, d.p1, 0); L1.p1 = xy_merge1(c.p1, d.p1, 1);
-    L0.p2 = xy_merge1(c.p2, d.p2, 0); L1.p2 = xy_merge1(c.p2, d.p2, 1);
+    // new values of the next word's voxel 0: bit 7 of the right words' bytes 2 (row 0) and 3 (row 1)
+    const uint32_t c2 = prmt(b.p2, d.p2, 0x7632);        // bit 7, 15: U.p2 rows 0, 1; bit 23, 31: L.p2 rows 0, 1
+    carry = (shr<7>(prmt(b.p0, b.p1, 0x7632)) & 0x01010101u) | (shr<6>(prmt(d.p0, d.p1, 0x7632)) & 0x02020202u) |
+            (shr<5>(c2) & 0x0404u) | (shr<20>(c2) & 0x0808u);
+    // the words are finished by xy3_pair_post1 (see xy_pair_substep1 in bitslice.cuh)
+    U0.p0 = prmt(a.p0, b.p0, 0x2406); U1.p0 = prmt(a.p0, b.p0, 0x3517);
+    U0.p1 = prmt(a.p1, b.p1, 0x2406); U1.p1 = prmt(a.p1, b.p1, 0x3517);
+    U0.p2 = prmt(a.p2, b.p2, 0x2406); U1.p2 = prmt(a.p2, b.p2, 0x3517);
+    L0.p0 = prmt(c.p0, d.p0, 0x2406); L1.p0 = prmt(c.p0, d.p0, 0x3517);
+    L0.p1 = prmt(c.p1, d.p1, 0x2406); L1.p1 = prmt(c.p1, d.p1, 0x3517);
+    L0.p2 = prmt(c.p2, d.p2, 0x2406); L1.p2 = prmt(c.p2, d.p2, 0x3517);
     return en;
 }
 FS3D_HD void xy3_pair_post1(P3 &U0, P3 &L0, P3 &U1, P3 &L1, uint32_t pb) {
-    U0.p0 |= pb & 1u;         U1.p0 |= (pb >> 1) & 1u;  U0.p1 |= (pb >> 2) & 1u;  U1.p1 |= (pb >> 3) & 1u;
-    U0.p2 |= (pb >> 4) & 1u;  U1.p2 |= (pb >> 5) & 1u;
-    L0.p0 |= (pb >> 6) & 1u;  L1.p0 |= (pb >> 7) & 1u;  L0.p1 |= (pb >> 8) & 1u;  L1.p1 |= (pb >> 9) & 1u;
-    L0.p2 |= (pb >> 10) & 1u; L1.p2 |= (pb >> 11) & 1u;
+    const uint32_t cu = pb & 0x01010101u, cl = shr<1>(pb) & 0x01010101u, cu2 = shr<2>(pb) & 0x0101u, cl2 = shr<3>(pb) & 0x0101u;
+    U0.p0 = xy_finish1(U0.p0, cu);  U1.p0 = xy_finish1(U1.p0, shr<8>(cu));  U0.p1 = xy_finish1(U0.p1, shr<16>(cu)); U1.p1 = xy_finish1(U1.p1, shr<24>(cu));
+    L0.p0 = xy_finish1(L0.p0, cl);  L1.p0 = xy_finish1(L1.p0, shr<8>(cl));  L0.p1 = xy_finish1(L0.p1, shr<16>(cl)); L1.p1 = xy_finish1(L1.p1, shr<24>(cl));
+    U0.p2 = xy_finish1(U0.p2, cu2); U1.p2 = xy_finish1(U1.p2, shr<8>(cu2));
+    L0.p2 = xy_finish1(L0.p2, cl2); L1.p2 = xy_finish1(L1.p2, shr<8>(cl2));
 }
 // voxel 0 of a row's first word (global x = 0) under odd x-offset: the block's left column is the wall, so only F
 // applies (the wall is STONE: D needs a non-STONE neighbour beside the mover, L two yielding cells).  `first` = the
 // cells' bits before the sub-step (xy3_first_bits); returns their new values; en |= rows whose block is enabled.
 FS3D_HD uint32_t xy3_wall_first(uint32_t first, uint32_t &en) {
-    P3 u{first & 3u, (first >> 2) & 3u, (first >> 4) & 3u}, l{(first >> 6) & 3u, (first >> 8) & 3u, (first >> 10) & 3u};   // bit r = row r
-    const uint32_t h = heavier3(u, l) & 3u;
-    cswap3(h, u, l);
+    // both rows at once, aligned to bits 0 (row 0) and 8 (row 1); the other bits are garbage and masked out of h
+    const P3 u{first, shr<16>(first), shr<2>(first)}, l{shr<1>(first), shr<17>(first), shr<3>(first)};
+    const uint32_t h = heavier3(u, l) & 0x0101u;
     en |= h;
-    return (u.p0 & 3u) | ((u.p1 & 3u) << 2) | ((u.p2 & 3u) << 4) | ((l.p0 & 3u) << 6) | ((l.p1 & 3u) << 8) | ((l.p2 & 3u) << 10);
+    // the U and L bit of a plane flip together where the cells swap and differ in that plane
+    const uint32_t t0 = (u.p0 ^ l.p0) & h, t1 = (u.p1 ^ l.p1) & h, t2 = (u.p2 ^ l.p2) & h;
+    return first ^ ((t0 + shl_add<2>(t2, 0u) + shl_add<16>(t1, 0u)) * 3u);
 }
 
 }  // namespace fs3d

@@ -54,7 +54,7 @@ struct Rules3 {
     using Cell = P3;
     static constexpr bool COLUMN_FORM = false;
     static constexpr uint32_t NB_STONE = NB_STONE3;
-    static constexpr bool EDGE_TOLERANT = false;
+    static constexpr bool EDGE_TOLERANT = true;
     static __device__ __forceinline__ Cell stone() { return {ONES, ONES, ONES}; }
     static __device__ __forceinline__ Cell pack(const uint32_t (&w)[8]) { return pack3(w); }
     static __device__ __forceinline__ void unpack(Cell c, uint32_t (&w)[8]) { unpack3(c, w); }

@@ -68,6 +68,9 @@ static const P3 STONE3 = {ONES, ONES, ONES};
 static P3 rdw(Grid &g, int z, int y, int xw) { if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) return STONE3; return g.at(z, y, xw); }
 static void wrw(Grid &g, int z, int y, int xw, P3 v) { if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) return; g.at(z, y, xw) = v; }
 
+// the exchanged edge words are byte-packed (bitslice3.cuh): every bit outside NB_STONE3 is "don't care" — the kernels put
+// the mailbox tag there — so the emulation sets them all
+static const uint32_t GARBAGE3 = ~NB_STONE3;
 template <int OX>
 static void emu_xy_pair(Grid &g, uint32_t key, int oy) {
     for (int z = 0; z < g.nz; z += 2)
@@ -82,12 +85,12 @@ static void emu_xy_pair(Grid &g, uint32_t key, int oy) {
             }
             for (int xw = 0; xw < W; ++xw) {
                 if (OX == 0) xy3_pair_substep0(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw]);
-                else xy3_pair_substep1(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw], xw + 1 < W ? first[xw + 1] : NB_STONE3, carry[xw]);
+                else xy3_pair_substep1(U0[xw], L0[xw], U1[xw], L1[xw], r0[xw], r1[xw], xw + 1 < W ? (first[xw + 1] | GARBAGE3) : NB_STONE3, carry[xw]);
             }
             if (OX == 1)
                 for (int xw = 0; xw < W; ++xw) {
                     uint32_t en = 0;
-                    xy3_pair_post1(U0[xw], L0[xw], U1[xw], L1[xw], xw > 0 ? carry[xw - 1] : xy3_wall_first(first[0], en));
+                    xy3_pair_post1(U0[xw], L0[xw], U1[xw], L1[xw], xw > 0 ? (carry[xw - 1] | GARBAGE3) : xy3_wall_first(first[0] | GARBAGE3, en));
                 }
             for (int xw = 0; xw < W; ++xw) {
                 wrw(g, z, y0 + 1, xw, U0[xw]); wrw(g, z, y0, xw, L0[xw]); wrw(g, z + 1, y0 + 1, xw, U1[xw]); wrw(g, z + 1, y0, xw, L1[xw]);
